@@ -1,0 +1,462 @@
+// abi.cu -- the C ABI of include/strided_b200.h: context, plan cache, launches, host staging.
+//
+// There is NO CPU execution path here: without a CUDA device every compute entry point returns
+// SB_E_NODEVICE.  (sb_plan_describe is pure host planning and works anywhere.)
+#include "kernels.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include <algorithm>
+
+using namespace sb;
+
+namespace sb {
+
+static const MapEntry *lookup_map(const MapEntry *tab, int n, const KernelKey &k)
+{
+    for (int i = 0; i < n; ++i) {
+        const KernelKey &e = tab[i].key;
+        if (e.ct == k.ct && e.recipe == k.recipe && e.nin == k.nin && e.ept == k.ept && e.uniform == k.uniform) return &tab[i];
+    }
+    return nullptr;
+}
+static const ReduceEntry *lookup_red(const ReduceEntry *tab, int n, const KernelKey &k)
+{
+    for (int i = 0; i < n; ++i) {
+        const KernelKey &e = tab[i].key;
+        if (e.ct == k.ct && e.recipe == k.recipe && e.nin == k.nin && e.ept == k.ept && e.uniform == k.uniform) return &tab[i];
+    }
+    return nullptr;
+}
+const MapEntry *find_map_kernel(const KernelKey &k)
+{
+    int n = 0;
+    const MapEntry *t = k.ct == F32 ? map_table_f32(&n) : k.ct == F64 ? map_table_f64(&n) : k.ct == C32 ? map_table_c32(&n) : map_table_c64(&n);
+    return lookup_map(t, n, k);
+}
+const ReduceEntry *find_reduce_kernel(const KernelKey &k)
+{
+    int n = 0;
+    const ReduceEntry *t = k.ct == F32 ? reduce_table_f32(&n) : k.ct == F64 ? reduce_table_f64(&n) : k.ct == C32 ? reduce_table_c32(&n) : reduce_table_c64(&n);
+    return lookup_red(t, n, k);
+}
+
+} // namespace sb
+
+static thread_local std::string g_tls_err;
+
+struct sb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    bool sync = true;
+    DeviceInfo dev;
+    std::mutex mu;
+    std::string err;
+    sb_stats stats{};
+    // reduce partials
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // occupancy cache: kernel function -> (smem -> blocks/SM)
+    std::map<std::pair<const void *, size_t>, int> occ;
+    // host staging pool (sb_mapreduce_host)
+    void *stage = nullptr;
+    size_t stage_bytes = 0;
+    std::unordered_map<std::string, Plan> plans;
+};
+
+static int set_err(sb_ctx *ctx, int code, const std::string &msg)
+{
+    g_tls_err = msg;
+    if (ctx) ctx->err = msg;
+    return code;
+}
+static int cuda_fail(sb_ctx *ctx, cudaError_t e, const char *what)
+{
+    return set_err(ctx, SB_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+extern "C" {
+
+int sb_abi_version(void) { return SB_ABI_VERSION; }
+
+const char *sb_last_error(sb_ctx *ctx)
+{
+    if (ctx) return ctx->err.c_str();
+    return g_tls_err.c_str();
+}
+
+int sb_ctx_create(int device, void *stream, sb_ctx **out)
+{
+    if (!out) return set_err(nullptr, SB_E_INVALID, "sb_ctx_create: null out");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return set_err(nullptr, SB_E_NODEVICE, "no CUDA device available: strided_b200 has no CPU execution path");
+    }
+    if (device < 0 || device >= ndev) return set_err(nullptr, SB_E_INVALID, "sb_ctx_create: bad device index");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+    sb_ctx *c = new (std::nothrow) sb_ctx();
+    if (!c) return set_err(nullptr, SB_E_NOMEM, "out of host memory");
+    c->device = device;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        delete c;
+        return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    }
+    c->dev.sm_count = prop.multiProcessorCount;
+    c->dev.ctas_per_sm = 4;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete c;
+            return cuda_fail(nullptr, e, "cudaStreamCreate");
+        }
+        c->own_stream = true;
+    }
+    *out = c;
+    return SB_OK;
+}
+
+int sb_ctx_destroy(sb_ctx *ctx)
+{
+    if (!ctx) return SB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->stage) cudaFree(ctx->stage);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return SB_OK;
+}
+
+int sb_ctx_set_stream(sb_ctx *ctx, void *stream)
+{
+    if (!ctx) return set_err(nullptr, SB_E_INVALID, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->own_stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+        ctx->own_stream = false;
+    }
+    ctx->stream = (cudaStream_t)stream;
+    return SB_OK;
+}
+
+int sb_ctx_set_sync(sb_ctx *ctx, int sync)
+{
+    if (!ctx) return set_err(nullptr, SB_E_INVALID, "null ctx");
+    ctx->sync = sync != 0;
+    return SB_OK;
+}
+
+int sb_sync(sb_ctx *ctx)
+{
+    if (!ctx) return set_err(nullptr, SB_E_INVALID, "null ctx");
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaStreamSynchronize");
+    return SB_OK;
+}
+
+int sb_malloc(sb_ctx *ctx, size_t bytes, void **out)
+{
+    if (!ctx || !out) return set_err(ctx, SB_E_INVALID, "sb_malloc: null argument");
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc");
+    return SB_OK;
+}
+int sb_free(sb_ctx *ctx, void *ptr)
+{
+    if (!ctx) return set_err(nullptr, SB_E_INVALID, "null ctx");
+    cudaError_t e = cudaFree(ptr);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFree");
+    return SB_OK;
+}
+int sb_memcpy_h2d(sb_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (!ctx) return set_err(nullptr, SB_E_INVALID, "null ctx");
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "memcpy h2d");
+    ctx->stats.h2d_bytes += bytes;
+    return SB_OK;
+}
+int sb_memcpy_d2h(sb_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (!ctx) return set_err(nullptr, SB_E_INVALID, "null ctx");
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "memcpy d2h");
+    ctx->stats.d2h_bytes += bytes;
+    return SB_OK;
+}
+
+int sb_get_stats(sb_ctx *ctx, sb_stats *out)
+{
+    if (!ctx || !out) return set_err(ctx, SB_E_INVALID, "null argument");
+    *out = ctx->stats;
+    return SB_OK;
+}
+int sb_reset_stats(sb_ctx *ctx)
+{
+    if (!ctx) return set_err(nullptr, SB_E_INVALID, "null ctx");
+    ctx->stats = sb_stats{};
+    return SB_OK;
+}
+
+int sb_plan_describe(sb_ctx *ctx, const sb_desc *desc, char *buf, size_t buflen)
+{
+    if (!desc || !buf || buflen == 0) return set_err(ctx, SB_E_INVALID, "sb_plan_describe: null argument");
+    Plan plan;
+    std::string err;
+    DeviceInfo dev = ctx ? ctx->dev : DeviceInfo{};
+    int rc = build_plan(*desc, dev, plan, err);
+    if (rc != SB_OK) return set_err(ctx, rc, err);
+    std::string s = describe_plan(plan);
+    std::snprintf(buf, buflen, "%s", s.c_str());
+    return SB_OK;
+}
+
+} // extern "C"
+
+// ---- launch -----------------------------------------------------------------------------------------------
+static int occupancy_of(sb_ctx *ctx, const void *func, cudaError_t (*occ)(int *, size_t), size_t smem, int &nb)
+{
+    auto key = std::make_pair(func, smem);
+    auto it = ctx->occ.find(key);
+    if (it != ctx->occ.end()) {
+        nb = it->second;
+        return SB_OK;
+    }
+    cudaError_t e = occ(&nb, smem);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "occupancy query");
+    if (nb < 1) nb = 1;
+    ctx->occ[key] = nb;
+    return SB_OK;
+}
+
+static int run_desc(sb_ctx *ctx, const sb_desc &desc)
+{
+    // plan cache: everything but the base pointers (the reference re-plans on every call; config 3 is ~2 us
+    // of device work, so planning must not be on the critical path)
+    sb_desc keyd = desc;
+    for (int k = 0; k < SB_MAX_OPS; ++k) keyd.base[k] = nullptr;
+    for (int i = keyd.ndim; i < SB_MAX_DIMS; ++i) keyd.dims[i] = 0;
+    for (int k = 0; k < SB_MAX_OPS; ++k)
+        for (int i = 0; i < SB_MAX_DIMS; ++i)
+            if (k >= keyd.nops || i >= keyd.ndim) keyd.strides[k][i] = 0;
+    for (int k = keyd.nops; k < SB_MAX_OPS; ++k) keyd.dtype[k] = keyd.conj[k] = 0;
+    for (int i = (keyd.ntok > 0 ? keyd.ntok : 0); i < SB_MAX_TOKENS; ++i) keyd.prog[i] = sb_tok{0, 0, 0.0, 0.0};
+    std::string key((const char *)&keyd, sizeof keyd);
+    int rc;
+    auto hit = ctx->plans.find(key);
+    if (hit == ctx->plans.end()) {
+        Plan fresh;
+        std::string err;
+        rc = build_plan(desc, ctx->dev, fresh, err);
+        if (rc != SB_OK) return set_err(ctx, rc, err);
+        ctx->stats.plans_built++;
+        if (ctx->plans.size() > 4096) ctx->plans.clear();
+        hit = ctx->plans.emplace(std::move(key), std::move(fresh)).first;
+    } else {
+        ctx->stats.plans_cached++;
+    }
+    Plan plan = hit->second; // copy: bases are bound per call
+    for (int k = 0; k < MAXO; ++k) {
+        plan.map.base[k] = (unsigned char *)desc.base[plan.base_src[k] < desc.nops ? plan.base_src[k] : 0];
+        plan.red.base[k] = plan.map.base[k];
+    }
+    if (plan.kind == PLAN_NOOP) return SB_OK;
+    cudaSetDevice(ctx->device);
+    if (plan.kind == PLAN_MAP) {
+        const MapEntry *k = find_map_kernel(plan.key);
+        if (!k) return set_err(ctx, SB_E_UNSUPPORTED, "no map kernel instantiated for this plan");
+        int nb = 1;
+        rc = occupancy_of(ctx, k->func, k->occupancy, (size_t)plan.smem_bytes, nb);
+        if (rc != SB_OK) return rc;
+        int64_t grid = std::min<int64_t>(plan.map.ntiles, (int64_t)ctx->dev.sm_count * nb);
+        if (grid < 1) grid = 1;
+        cudaError_t e = k->launch(plan.map, (int)grid, (size_t)plan.smem_bytes, ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "map_tile launch");
+        ctx->stats.launches++;
+    } else {
+        const ReduceEntry *k = find_reduce_kernel(plan.key);
+        if (!k) return set_err(ctx, SB_E_UNSUPPORTED, "no reduce kernel instantiated for this plan");
+        if ((size_t)plan.scratch_bytes > ctx->scratch_bytes) {
+            if (ctx->scratch) {
+                cudaStreamSynchronize(ctx->stream);
+                cudaFree(ctx->scratch);
+                ctx->scratch = nullptr;
+                ctx->scratch_bytes = 0;
+            }
+            size_t want = std::max<size_t>((size_t)plan.scratch_bytes, 1 << 20);
+            cudaError_t e = cudaMalloc(&ctx->scratch, want);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(scratch)");
+            ctx->scratch_bytes = want;
+        }
+        plan.red.scratch = (unsigned char *)ctx->scratch;
+        cudaError_t e = k->launch(plan.red, (int)plan.grid, (size_t)plan.smem_bytes, ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "reduce_tile launch");
+        ctx->stats.launches++;
+        if (plan.finalize_threads > 0) {
+            const int64_t g = (plan.finalize_threads + THREADS - 1) / THREADS;
+            e = k->finalize(plan.red, (int)g, ctx->stream);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "reduce_finalize launch");
+            ctx->stats.launches++;
+        }
+    }
+    return SB_OK;
+}
+
+extern "C" int sb_mapreduce(sb_ctx *ctx, const sb_desc *desc)
+{
+    if (!ctx) return set_err(nullptr, SB_E_INVALID, "sb_mapreduce: null ctx");
+    if (!desc) return set_err(ctx, SB_E_INVALID, "sb_mapreduce: null desc");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = run_desc(ctx, *desc);
+    if (rc != SB_OK) return rc;
+    if (ctx->sync) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "kernel execution");
+    }
+    return SB_OK;
+}
+
+// ---- host-resident operands ---------------------------------------------------------------------------------
+// Byte range touched by operand k: [lo, hi) relative to base[k].
+static void operand_range(const sb_desc &d, int k, int64_t &lo, int64_t &hi)
+{
+    const int es = dtype_size(d.dtype[k]);
+    int64_t mn = 0, mx = 0;
+    for (int i = 0; i < d.ndim; ++i) {
+        const int64_t ext = (d.dims[i] - 1) * d.strides[k][i];
+        if (ext < 0) mn += ext;
+        else mx += ext;
+    }
+    lo = mn * es;
+    hi = (mx + 1) * es;
+}
+
+extern "C" int sb_mapreduce_host(sb_ctx *ctx, const sb_desc *desc)
+{
+    if (!ctx) return set_err(nullptr, SB_E_INVALID, "sb_mapreduce_host: null ctx");
+    if (!desc) return set_err(ctx, SB_E_INVALID, "sb_mapreduce_host: null desc");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const sb_desc &d = *desc;
+    if (d.ndim < 0 || d.ndim > SB_MAX_DIMS || d.nops < 1 || d.nops > SB_MAX_OPS) return set_err(ctx, SB_E_INVALID, "bad ndim/nops");
+    for (int i = 0; i < d.ndim; ++i) {
+        if (d.dims[i] < 0) return set_err(ctx, SB_E_SHAPE, "negative dim");
+        if (d.dims[i] == 0) { // nothing is read; only the (rare) initop-on-empty case touches the output
+            sb_desc E;
+            if (!empty_initop_desc(d, E)) return SB_OK;
+            break;
+        }
+    }
+    for (int k = 0; k < d.nops; ++k)
+        if (d.dtype[k] < SB_F32 || d.dtype[k] > SB_C64) return set_err(ctx, SB_E_INVALID, "bad dtype");
+    // 1. host byte ranges per operand; merge overlapping ranges (aliased views of one parent) into segments
+    struct Seg {
+        uintptr_t lo, hi;
+        bool has_in, has_out;
+        size_t dev_off;
+    };
+    std::vector<Seg> segs;
+    uintptr_t olo[SB_MAX_OPS], ohi[SB_MAX_OPS];
+    bool any_zero = false;
+    for (int i = 0; i < d.ndim; ++i) any_zero |= d.dims[i] == 0;
+    for (int k = 0; k < d.nops; ++k) {
+        int64_t lo, hi;
+        if (any_zero) {
+            lo = 0;
+            hi = 0;
+            if (k == 0) { // output range of the initop-on-empty case: use kept dims only
+                sb_desc E;
+                empty_initop_desc(d, E);
+                operand_range(E, 0, lo, hi);
+            }
+        } else
+            operand_range(d, k, lo, hi);
+        olo[k] = (uintptr_t)d.base[k] + lo;
+        ohi[k] = (uintptr_t)d.base[k] + hi;
+        if (ohi[k] > olo[k]) segs.push_back(Seg{olo[k], ohi[k], k > 0, k == 0, 0});
+    }
+    std::sort(segs.begin(), segs.end(), [](const Seg &a, const Seg &b) { return a.lo < b.lo; });
+    std::vector<Seg> merged;
+    for (const Seg &s : segs) {
+        if (!merged.empty() && s.lo < merged.back().hi) {
+            merged.back().hi = std::max(merged.back().hi, s.hi);
+            merged.back().has_in |= s.has_in;
+            merged.back().has_out |= s.has_out;
+        } else
+            merged.push_back(s);
+    }
+    size_t total = 0;
+    for (Seg &s : merged) {
+        s.dev_off = total;
+        total += ((s.hi - s.lo) + 255) & ~(size_t)255;
+    }
+    cudaSetDevice(ctx->device);
+    if (total > ctx->stage_bytes) {
+        if (ctx->stage) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(ctx->stage);
+            ctx->stage = nullptr;
+            ctx->stage_bytes = 0;
+        }
+        cudaError_t e = cudaMalloc(&ctx->stage, total);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(stage)");
+        ctx->stage_bytes = total;
+    }
+    // 2. does the output need its previous contents on the device?  yes if it is read (op / initop) or if
+    //    the written elements do not cover its byte range densely (strided destination)
+    bool out_dense = !any_zero;
+    if (out_dense) {
+        int64_t cnt = 1;
+        for (int i = 0; i < d.ndim; ++i)
+            if (d.strides[0][i] != 0) cnt *= d.dims[i];
+        out_dense = (uintptr_t)(cnt * dtype_size(d.dtype[0])) == (ohi[0] - olo[0]);
+    }
+    const bool out_read = d.op != SB_OP_NONE || !out_dense;
+    for (const Seg &s : merged) {
+        if (!(s.has_in || (s.has_out && out_read))) continue;
+        cudaError_t e = cudaMemcpyAsync((char *)ctx->stage + s.dev_off, (const void *)s.lo, s.hi - s.lo, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "stage h2d");
+        ctx->stats.h2d_bytes += s.hi - s.lo;
+    }
+    // 3. run on device pointers
+    sb_desc dd = d;
+    for (int k = 0; k < d.nops; ++k) {
+        const Seg *home = nullptr;
+        for (const Seg &s : merged)
+            if (olo[k] >= s.lo && olo[k] < s.hi) home = &s;
+        if (!home) { // empty range (zero-size problem)
+            dd.base[k] = ctx->stage;
+            continue;
+        }
+        dd.base[k] = (char *)ctx->stage + home->dev_off + ((uintptr_t)d.base[k] - home->lo);
+    }
+    int rc = run_desc(ctx, dd);
+    if (rc != SB_OK) return rc;
+    // 4. output back
+    for (const Seg &s : merged) {
+        if (!s.has_out) continue;
+        cudaError_t e = cudaMemcpyAsync((void *)s.lo, (char *)ctx->stage + s.dev_off, s.hi - s.lo, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "stage d2h");
+        ctx->stats.d2h_bytes += s.hi - s.lo;
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "sb_mapreduce_host");
+    return SB_OK;
+}

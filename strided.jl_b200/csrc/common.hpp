@@ -1,0 +1,161 @@
+// common.hpp -- PODs shared by the host planner and the sm_100a kernels.
+//
+// Design: every `_mapreduce_fuse!` call (reference src/mapreduce.jl:98) becomes a
+// *tile plan*.  The index space is cut into power-of-two boxes ("tiles"); a CTA of THREADS threads owns a
+// tile and each thread owns EPT elements `lin = t + j*THREADS` of it.  Because all tile extents and
+// THREADS are powers of two, the coordinates of `lin` under ANY traversal order split into bit fields that
+// come either from `t` or from `j`, so every address functional (global offset, shared-memory slot) is
+//     F(t, j) = toff(t) + joff[j]
+// with toff computed once per thread and joff a small table in kernel-parameter space.  Each operand is
+// loaded in ITS OWN fastest-stride order (coalesced), staged through shared memory when that order differs
+// from the output's, and consumed in the output's order.  This replaces the reference's cache-blocked loop
+// nest `_mapreduce_kernel!` (src/mapreduce.jl:229-425) and its task bisection (:195-227).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SB_HD __host__ __device__ __forceinline__
+#define SB_D __device__ __forceinline__
+#else
+#define SB_HD inline
+#define SB_D inline
+#endif
+
+namespace sb {
+
+constexpr int MAXD = 8;    // SB_MAX_DIMS
+constexpr int MAXO = 8;    // SB_MAX_OPS (operand 0 = output)
+constexpr int MAXIN = MAXO - 1;
+constexpr int MAXTD = 6;   // tile dims with extent > 1
+constexpr int MAXEPT = 16; // elements per thread per tile
+constexpr int THREADS = 256;
+constexpr int LOG_THREADS = 8;
+constexpr int MAXTOK = 48;
+
+enum DType : int { F32 = 0, F64 = 1, C32 = 2, C64 = 3 };
+SB_HD int dtype_size(int dt) { return dt == F32 ? 4 : (dt == C64 ? 16 : 8); }
+
+// ---- element program ------------------------------------------------------------------------------
+enum TokKind : int { TOK_ARG = 0, TOK_CONST = 1, TOK_CALL = 2 };
+enum Fn : int {
+    FN_IDENTITY = 0, FN_NEG = 1, FN_CONJ = 2, FN_ABS = 3, FN_ABS2 = 4, FN_REAL = 5, FN_IMAG = 6, FN_SQRT = 7,
+    FN_EXP = 8, FN_LOG = 9, FN_SIN = 10, FN_COS = 11, FN_TANH = 12, FN_INV = 13,
+    FN_ADD = 32, FN_SUB = 33, FN_MUL = 34, FN_DIV = 35, FN_MAX = 36, FN_MIN = 37, FN_LT = 38
+};
+enum RedOp : int { OP_NONE = 0, OP_ADD = 1, OP_MUL = 2, OP_MIN = 3, OP_MAX = 4 };
+enum InitOp : int { INIT_NONE = 0, INIT_ZERO = 1, INIT_IDENTITY = 2, INIT_SCALE = 3, INIT_CONST = 4, INIT_CONJ = 5 };
+
+struct Tok {
+    int32_t kind;
+    int32_t a;
+    double re, im;
+};
+
+// Pre-instantiated element functions ("recipes"): Julia specialises `_mapreduce_kernel!` on `f`
+// (it is @generated on the callable's type); a precompiled engine cannot, so the planner pattern-matches
+// the program against these and falls back to the in-kernel interpreter otherwise.
+enum Recipe : int {
+    RC_INTERP = 0,   // generic postfix interpreter
+    RC_COPY,         // x0                           copy!/permutedims!/adjoint!       mapreduce.jl:2-14
+    RC_SCALE,        // c0 * x0                      C1  `3 .* A'`, rmul!/lmul!        linalg.jl:2-3
+    RC_ADD2,         // x0 + x1
+    RC_ADD2_DIV,     // (x0 + x1) / c0               C2  `(A .+ A') ./ 2`
+    RC_ADD2_MUL,     // (x0 + x1) * c0
+    RC_SUM3,         // (x0 + x1) + x2
+    RC_SUM4,         // ((x0 + x1) + x2) + x3        C4  4-way permutedims sum
+    RC_AXPY,         // c0 * x0 + x1                 axpy!                             linalg.jl:23-31
+    RC_AXPBY,        // c0 * x0 + c1 * x1            axpby!                            linalg.jl:32-42
+    RC_ABS2,         // abs2(x0)                     C5  mapreduce(abs2, +, A; dims)
+    RC_COUNT_
+};
+
+struct Program {
+    int32_t recipe;
+    int32_t ntok;
+    double c0re, c0im, c1re, c1im; // recipe constants
+    Tok tok[MAXTOK];
+};
+
+// ---- traversal order of a tile ---------------------------------------------------------------------
+// slot i of an order covers bits [shift[i], shift[i]+bits[i]) of the in-tile linear index and is the
+// coordinate along tile-dim `td[i]` (an index into MapPlan::tdim).
+struct OrderTab {
+    uint8_t n;
+    uint8_t td[MAXTD];
+    uint8_t shift[MAXTD];
+    uint8_t bits[MAXTD];
+};
+
+// ---- map plan (kernel parameter block) -------------------------------------------------------------
+struct MapParams {
+    int32_t ndim;  // canonical dims (size-1 dropped, fused, sorted by |output stride|)
+    int32_t nops;  // output + inputs
+    int32_t ntd;   // tile dims (extent > 1)
+    int32_t nstaged;
+    int64_t dims[MAXD];
+    int32_t tile_b[MAXD]; // tile extent per canonical dim (1 for grid-only dims)
+    int32_t ntile[MAXD];  // ceil(dims/tile_b)
+    uint8_t tdim[MAXTD];  // tile-dim slot -> canonical dim
+    int64_t ntiles;
+    const int32_t *tile_order; // optional device table: launch position -> tile id (alias-aware order)
+    unsigned char *base[MAXO];
+    int64_t strides[MAXO][MAXD]; // elements
+    uint8_t dtype[MAXO];
+    uint8_t conj[MAXO];
+    uint8_t staged[MAXO];  // 1: loaded in own order, transposed through shared memory
+    OrderTab order[MAXO];  // order[0] = output order; order[k] = load order of operand k
+    int64_t g_tstr[MAXO][MAXTD]; // global element stride per order slot (for toff)
+    int64_t g_joff[MAXO][MAXEPT];
+    int32_t w_tstr[MAXO][MAXTD]; // shared-memory slot stride per OWN-order slot (staged operands)
+    int32_t w_joff[MAXO][MAXEPT];
+    int32_t r_tstr[MAXO][MAXTD]; // shared-memory slot stride per OUTPUT-order slot
+    int32_t r_joff[MAXO][MAXEPT];
+    int32_t smem_off[MAXO];      // element offset of the operand's staging buffer (units of CT)
+    uint16_t jfield[MAXO][MAXEPT][MAXTD]; // coordinate bits contributed by j, per order slot
+    int32_t ept;
+    int32_t uniform; // all dtypes == compute type and no conj flags
+    Program prog;
+};
+
+// ---- reduce plan ------------------------------------------------------------------------------------
+struct ReduceParams {
+    int32_t ndim, nops, ntd;
+    int32_t nkept;               // canonical dims [0, nkept) are kept, [nkept, ndim) reduced
+    int64_t dims[MAXD];
+    int32_t tile_b[MAXD];
+    int32_t ntile[MAXD];
+    uint8_t tdim[MAXTD];
+    int64_t nouttiles;           // product of ntile over kept dims
+    int64_t nrsteps;             // product of ntile over reduced dims
+    int64_t steps_per_split;
+    int32_t nsplit;
+    unsigned char *base[MAXO];
+    int64_t strides[MAXO][MAXD];
+    uint8_t dtype[MAXO];
+    uint8_t conj[MAXO];
+    OrderTab order;              // load order (input 1's fastest-stride order) over ALL tile dims
+    int64_t g_tstr[MAXO][MAXTD];
+    int64_t g_joff[MAXO][MAXEPT];
+    uint16_t jfield[MAXEPT][MAXTD];
+    int32_t s_tstr[MAXTD];       // shared-memory slot of (t, j) for the final in-CTA combine
+    int32_t s_joff[MAXEPT];
+    int32_t nout_tile;           // outputs per tile  = prod of kept tile extents
+    int32_t nred_tile;           // partials per output = E / nout_tile
+    int32_t warp_per_output;     // 1: layout [o][r], warp folds one output; 0: layout [r][o], thread per output
+    OrderTab kept_order;         // decode of output number o -> kept tile coords (output order)
+    unsigned char *scratch;      // partials [nsplit][nouttiles][nout_tile] of the ACCUMULATOR type
+    int32_t ept;
+    int32_t uniform;
+    int32_t op;
+    int32_t initop;
+    double init_re, init_im;
+    Program prog;
+};
+
+// ---- small HD helpers ---------------------------------------------------------------------------------
+SB_HD int field_of(const OrderTab &o, int slot, int lin)
+{
+    return (lin >> o.shift[slot]) & ((1 << o.bits[slot]) - 1);
+}
+
+} // namespace sb

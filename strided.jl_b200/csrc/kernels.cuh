@@ -1,0 +1,158 @@
+// kernels.cuh -- __global__ wrappers (sm_100a) around the tile bodies + the launch registry.
+#pragma once
+#include "map_tile.hpp"
+#include "reduce_tile.hpp"
+#include "planner.hpp"
+#include <cuda_runtime.h>
+
+namespace sb {
+
+// ---- map ------------------------------------------------------------------------------------------------
+// Persistent CTAs: grid = min(ntiles, SMs x resident CTAs); each CTA walks tiles pos = blockIdx.x + i*grid,
+// so neighbouring CTAs work on neighbouring tiles at the same time (DRAM page / L2 locality, and aliased
+// operands such as A and A' meet in L2).
+template <class CT, int RC, int NIN, int EPT, bool UNIFORM>
+__global__ void __launch_bounds__(THREADS) map_tile_kernel(const __grid_constant__ MapParams P)
+{
+    extern __shared__ __align__(16) unsigned char sb_smem_raw[];
+    CT *smem = reinterpret_cast<CT *>(sb_smem_raw);
+    const int t = threadIdx.x;
+    MapThread<NIN + 1> th;
+    map_thread_init<NIN + 1>(P, t, th);
+    const bool staged = P.nstaged > 0;
+    for (int64_t pos = blockIdx.x; pos < P.ntiles; pos += gridDim.x) {
+        MapTile tl;
+        map_tile_init(P, pos, tl);
+        CT v[NIN][EPT];
+        map_phase1<CT, NIN, EPT, UNIFORM>(P, th, tl, t, v, smem);
+        if (staged) __syncthreads();
+        map_phase2<CT, RC, NIN, EPT, UNIFORM>(P, th, tl, t, v, smem);
+        if (staged) __syncthreads();
+    }
+}
+
+// ---- reduce ---------------------------------------------------------------------------------------------
+template <class T> __device__ __forceinline__ T shfl_xor_any(T v, int mask)
+{
+    constexpr int W = sizeof(T) / 4;
+    union {
+        T v;
+        uint32_t w[W];
+    } a, b;
+    a.v = v;
+#pragma unroll
+    for (int i = 0; i < W; ++i) b.w[i] = __shfl_xor_sync(0xffffffffu, a.w[i], mask);
+    return b.v;
+}
+
+template <class AT, int RC, int NIN, int EPT, bool UNIFORM>
+__global__ void __launch_bounds__(THREADS) reduce_tile_kernel(const __grid_constant__ ReduceParams P)
+{
+    extern __shared__ __align__(16) unsigned char sb_smem_raw[];
+    AT *smem = reinterpret_cast<AT *>(sb_smem_raw);
+    const int t = threadIdx.x;
+    const int64_t bid = blockIdx.x;
+    red_accumulate<AT, RC, NIN, EPT, UNIFORM>(P, bid, t, smem);
+    __syncthreads();
+    if (P.warp_per_output) {
+        const int warp = t >> 5, lane = t & 31;
+        for (int o = warp; o < P.nout_tile; o += THREADS / 32) {
+            AT p = red_lane_partial<AT>(P, smem, o, lane);
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) p = red_apply<AT>(P.op, p, shfl_xor_any(p, m));
+            if (lane == 0) red_finish<AT, UNIFORM>(P, bid, o, p);
+        }
+    } else {
+        for (int o = t; o < P.nout_tile; o += THREADS) red_finish<AT, UNIFORM>(P, bid, o, red_thread_partial<AT>(P, smem, o));
+    }
+}
+
+template <class AT, bool UNIFORM> __global__ void __launch_bounds__(THREADS) reduce_finalize_kernel(const __grid_constant__ ReduceParams P)
+{
+    const int64_t idx = (int64_t)blockIdx.x * THREADS + threadIdx.x;
+    red_finalize<AT, UNIFORM>(P, idx);
+}
+
+// ---- registry ---------------------------------------------------------------------------------------------
+struct MapEntry {
+    KernelKey key;
+    cudaError_t (*launch)(const MapParams &, int grid, size_t smem, cudaStream_t);
+    cudaError_t (*occupancy)(int *nblocks, size_t smem);
+    const void *func;
+};
+struct ReduceEntry {
+    KernelKey key;
+    cudaError_t (*launch)(const ReduceParams &, int grid, size_t smem, cudaStream_t);
+    cudaError_t (*finalize)(const ReduceParams &, int grid, cudaStream_t);
+    cudaError_t (*occupancy)(int *nblocks, size_t smem);
+    const void *func;
+};
+
+template <class CT, int RC, int NIN, int EPT, bool U> struct MapLaunch {
+    static cudaError_t launch(const MapParams &P, int grid, size_t smem, cudaStream_t s)
+    {
+        auto k = map_tile_kernel<CT, RC, NIN, EPT, U>;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        k<<<grid, THREADS, smem, s>>>(P);
+        return cudaGetLastError();
+    }
+    static cudaError_t occupancy(int *nb, size_t smem)
+    {
+        auto k = map_tile_kernel<CT, RC, NIN, EPT, U>;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, THREADS, smem);
+    }
+    static const void *func() { return (const void *)map_tile_kernel<CT, RC, NIN, EPT, U>; }
+};
+
+template <class AT, int RC, int NIN, int EPT, bool U> struct ReduceLaunch {
+    static cudaError_t launch(const ReduceParams &P, int grid, size_t smem, cudaStream_t s)
+    {
+        auto k = reduce_tile_kernel<AT, RC, NIN, EPT, U>;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        k<<<grid, THREADS, smem, s>>>(P);
+        return cudaGetLastError();
+    }
+    static cudaError_t finalize(const ReduceParams &P, int grid, cudaStream_t s)
+    {
+        reduce_finalize_kernel<AT, U><<<grid, THREADS, 0, s>>>(P);
+        return cudaGetLastError();
+    }
+    static cudaError_t occupancy(int *nb, size_t smem)
+    {
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, reduce_tile_kernel<AT, RC, NIN, EPT, U>, THREADS, smem);
+    }
+    static const void *func() { return (const void *)reduce_tile_kernel<AT, RC, NIN, EPT, U>; }
+};
+
+#define SB_MAP_ENTRY(CT, DT, RC, NIN, EPT, U)                                                                        \
+    MapEntry { KernelKey{DT, RC, NIN, EPT, U}, &MapLaunch<CT, RC, NIN, EPT, (U) != 0>::launch,                       \
+               &MapLaunch<CT, RC, NIN, EPT, (U) != 0>::occupancy, MapLaunch<CT, RC, NIN, EPT, (U) != 0>::func() }
+#define SB_RED_ENTRY(CT, DT, RC, NIN, EPT, U)                                                                        \
+    ReduceEntry { KernelKey{DT, RC, NIN, EPT, U}, &ReduceLaunch<CT, RC, NIN, EPT, (U) != 0>::launch,                 \
+                  &ReduceLaunch<CT, RC, NIN, EPT, (U) != 0>::finalize,                                               \
+                  &ReduceLaunch<CT, RC, NIN, EPT, (U) != 0>::occupancy, ReduceLaunch<CT, RC, NIN, EPT, (U) != 0>::func() }
+
+// one table per compute type, each in its own translation unit (parallel nvcc)
+const MapEntry *map_table_f32(int *n);
+const MapEntry *map_table_f64(int *n);
+const MapEntry *map_table_c32(int *n);
+const MapEntry *map_table_c64(int *n);
+const ReduceEntry *reduce_table_f32(int *n);
+const ReduceEntry *reduce_table_f64(int *n);
+const ReduceEntry *reduce_table_c32(int *n);
+const ReduceEntry *reduce_table_c64(int *n);
+
+const MapEntry *find_map_kernel(const KernelKey &k);
+const ReduceEntry *find_reduce_kernel(const KernelKey &k);
+
+} // namespace sb

@@ -1,0 +1,882 @@
+// planner.cpp -- see planner.hpp.  Pure host C++ (no CUDA): unit-tested on CPU through sb_plan_describe and
+// through the thread-grid emulator in tests/emul/.
+#include "planner.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+#include <vector>
+
+namespace sb {
+
+namespace {
+
+struct Canon {
+    int ndim = 0, nops = 0, nkept = 0;
+    int64_t dims[MAXD] = {0};
+    int64_t strides[MAXO][MAXD] = {{0}};
+    unsigned char *base[MAXO] = {nullptr};
+    int dtype[MAXO] = {0};
+    int conj[MAXO] = {0};
+    int op = OP_NONE, initop = INIT_NONE;
+    double init_re = 0, init_im = 0;
+    int ntok = 0;
+    Tok tok[MAXTOK];
+    int ct = F64;
+    int src[MAXO] = {0, 1, 2, 3, 4, 5, 6, 7}; // canonical operand -> sb_desc operand (plan cache re-binds bases)
+};
+
+int64_t iabs64(int64_t x) { return x < 0 ? -x : x; }
+int ilog2_ceil(int64_t x)
+{
+    int b = 0;
+    while (((int64_t)1 << b) < x) ++b;
+    return b;
+}
+
+bool is_cplx(int dt) { return dt == C32 || dt == C64; }
+bool is_dbl(int dt) { return dt == F64 || dt == C64; }
+
+// ---- program checks ---------------------------------------------------------------------------------
+int check_program(const Canon &c, std::string &err, int &maxdepth)
+{
+    int sp = 0;
+    maxdepth = 0;
+    for (int i = 0; i < c.ntok; ++i) {
+        const Tok &t = c.tok[i];
+        if (t.kind == TOK_ARG) {
+            if (t.a < 0 || t.a >= c.nops - 1) { err = "program: ARG index out of range"; return SB_E_INVALID; }
+            ++sp;
+        } else if (t.kind == TOK_CONST) {
+            ++sp;
+        } else if (t.kind == TOK_CALL) {
+            const bool unary = (t.a >= FN_IDENTITY && t.a <= FN_INV);
+            const bool binary = (t.a >= FN_ADD && t.a <= FN_LT);
+            if (!unary && !binary) { err = "program: unknown function id"; return SB_E_INVALID; }
+            const int ar = unary ? 1 : 2;
+            if (sp < ar) { err = "program: stack underflow"; return SB_E_INVALID; }
+            sp -= ar - 1;
+        } else {
+            err = "program: bad token kind";
+            return SB_E_INVALID;
+        }
+        maxdepth = std::max(maxdepth, sp);
+    }
+    if (c.ntok > 0 && sp != 1) { err = "program: must leave exactly one value"; return SB_E_INVALID; }
+    if (c.ntok == 0 && c.nops < 2) { err = "identity program needs an input"; return SB_E_INVALID; }
+    return SB_OK;
+}
+
+bool tok_arg(const Tok &t, int a) { return t.kind == TOK_ARG && t.a == a; }
+bool tok_call(const Tok &t, int fn) { return t.kind == TOK_CALL && t.a == fn; }
+bool tok_const(const Tok &t) { return t.kind == TOK_CONST; }
+bool is_pow2_double(double c)
+{
+    if (c == 0.0 || !std::isfinite(c)) return false;
+    int e;
+    const double m = std::frexp(std::fabs(c), &e);
+    return m == 0.5 && e > -1000 && e < 1000;
+}
+
+void match_recipe(const Canon &c, Program &p)
+{
+    p.recipe = RC_INTERP;
+    p.ntok = c.ntok;
+    p.c0re = p.c0im = p.c1re = p.c1im = 0;
+    for (int i = 0; i < c.ntok; ++i) p.tok[i] = c.tok[i];
+    const Tok *t = c.tok;
+    const int n = c.ntok, nin = c.nops - 1;
+    auto set0 = [&](const Tok &k) { p.c0re = k.re; p.c0im = k.im; };
+    auto set1 = [&](const Tok &k) { p.c1re = k.re; p.c1im = k.im; };
+    if (nin == 1 && (n == 0 || (n == 1 && tok_arg(t[0], 0)) || (n == 2 && tok_arg(t[0], 0) && tok_call(t[1], FN_IDENTITY)))) {
+        p.recipe = RC_COPY;
+    } else if (nin == 1 && n == 3 && tok_const(t[0]) && tok_arg(t[1], 0) && tok_call(t[2], FN_MUL)) {
+        p.recipe = RC_SCALE; set0(t[0]);
+    } else if (nin == 1 && n == 3 && tok_arg(t[0], 0) && tok_const(t[1]) && tok_call(t[2], FN_MUL) && t[1].im == 0.0) {
+        p.recipe = RC_SCALE; set0(t[1]); // x*c == c*x bitwise for real c
+    } else if (nin == 1 && n == 2 && tok_arg(t[0], 0) && tok_call(t[1], FN_ABS2)) {
+        p.recipe = RC_ABS2;
+    } else if (nin == 2 && n == 3 && tok_arg(t[0], 0) && tok_arg(t[1], 1) && tok_call(t[2], FN_ADD)) {
+        p.recipe = RC_ADD2;
+    } else if (nin == 2 && n == 5 && tok_arg(t[0], 0) && tok_arg(t[1], 1) && tok_call(t[2], FN_ADD) && tok_const(t[3]) &&
+               (tok_call(t[4], FN_DIV) || tok_call(t[4], FN_MUL))) {
+        set0(t[3]);
+        if (tok_call(t[4], FN_MUL)) p.recipe = RC_ADD2_MUL;
+        else if (t[3].im == 0.0 && is_pow2_double(t[3].re)) { // x / 2^k == x * 2^-k exactly (both correctly rounded)
+            p.recipe = RC_ADD2_MUL;
+            p.c0re = 1.0 / t[3].re;
+        } else p.recipe = RC_ADD2_DIV;
+    } else if (nin == 3 && n == 5 && tok_arg(t[0], 0) && tok_arg(t[1], 1) && tok_call(t[2], FN_ADD) && tok_arg(t[3], 2) &&
+               tok_call(t[4], FN_ADD)) {
+        p.recipe = RC_SUM3;
+    } else if (nin == 4 && n == 7 && tok_arg(t[0], 0) && tok_arg(t[1], 1) && tok_call(t[2], FN_ADD) && tok_arg(t[3], 2) &&
+               tok_call(t[4], FN_ADD) && tok_arg(t[5], 3) && tok_call(t[6], FN_ADD)) {
+        p.recipe = RC_SUM4;
+    } else if (nin == 2 && n == 5 && tok_const(t[0]) && tok_arg(t[1], 0) && tok_call(t[2], FN_MUL) && tok_arg(t[3], 1) &&
+               tok_call(t[4], FN_ADD)) {
+        p.recipe = RC_AXPY; set0(t[0]);
+    } else if (nin == 2 && n == 7 && tok_const(t[0]) && tok_arg(t[1], 0) && tok_call(t[2], FN_MUL) && tok_const(t[3]) &&
+               tok_arg(t[4], 1) && tok_call(t[5], FN_MUL) && tok_call(t[6], FN_ADD)) {
+        p.recipe = RC_AXPBY; set0(t[0]); set1(t[3]);
+    }
+}
+
+// ---- canonicalisation ---------------------------------------------------------------------------------
+int canonicalise(const sb_desc &d, Canon &c, bool &noop, std::string &err)
+{
+    noop = false;
+    if (d.ndim < 0 || d.ndim > SB_MAX_DIMS) { err = "ndim out of range"; return SB_E_INVALID; }
+    if (d.nops < 1 || d.nops > SB_MAX_OPS) { err = "nops out of range"; return SB_E_INVALID; }
+    if (d.ntok < 0 || d.ntok > SB_MAX_TOKENS) { err = "ntok out of range"; return SB_E_INVALID; }
+    if (d.op < SB_OP_NONE || d.op > SB_OP_MAX) { err = "bad op"; return SB_E_INVALID; }
+    if (d.initop < SB_INIT_NONE || d.initop > SB_INIT_CONJ) { err = "bad initop"; return SB_E_INVALID; }
+    for (int k = 0; k < d.nops; ++k)
+        if (d.dtype[k] < SB_F32 || d.dtype[k] > SB_C64) { err = "bad dtype"; return SB_E_INVALID; }
+    for (int i = 0; i < d.ndim; ++i)
+        if (d.dims[i] < 0) { err = "negative dim"; return SB_E_SHAPE; }
+
+    c.nops = d.nops;
+    c.op = d.op;
+    c.initop = (d.op == SB_OP_NONE) ? (int)INIT_NONE : d.initop;
+    c.init_re = d.init_re;
+    c.init_im = d.init_im;
+    c.ntok = d.ntok;
+    for (int i = 0; i < d.ntok; ++i) {
+        c.tok[i].kind = d.prog[i].kind;
+        c.tok[i].a = d.prog[i].a;
+        c.tok[i].re = d.prog[i].re;
+        c.tok[i].im = d.prog[i].im;
+    }
+    for (int k = 0; k < d.nops; ++k) {
+        c.base[k] = (unsigned char *)d.base[k];
+        c.dtype[k] = d.dtype[k];
+        c.conj[k] = d.conj[k] && is_cplx(d.dtype[k]);
+    }
+    if (c.op != OP_NONE && c.nops < 2) { err = "reduction without an input"; return SB_E_INVALID; }
+    int depth = 0;
+    int rc = check_program(c, err, depth);
+    if (rc != SB_OK) return rc;
+
+    // compute type: promote inputs and typed constants (Julia promotes per node; see DESIGN.md "compute type")
+    bool cplx = false, dbl = false;
+    for (int k = (c.nops > 1 ? 1 : 0); k < c.nops; ++k) {
+        cplx |= is_cplx(c.dtype[k]);
+        dbl |= is_dbl(c.dtype[k]);
+    }
+    for (int i = 0; i < c.ntok; ++i)
+        if (c.tok[i].kind == TOK_CONST) {
+            if (c.tok[i].im != 0.0) cplx = true;
+            if (c.tok[i].a == 2) dbl = true;
+        }
+    if (c.op != OP_NONE) {
+        cplx |= is_cplx(c.dtype[0]);
+        dbl |= is_dbl(c.dtype[0]);
+        if (c.initop == INIT_SCALE || c.initop == INIT_CONST)
+            if (c.init_im != 0.0) cplx = true;
+    }
+    c.ct = (cplx ? 2 : 0) + (dbl ? 1 : 0);
+
+    // zero-size dims: map! returns early (reference mapreduce.jl:48); _mapreducedim! applies initop to a
+    // non-empty output (:88-91) -- the latter is rewritten by the caller (abi) into a map; here: noop.
+    for (int i = 0; i < d.ndim; ++i)
+        if (d.dims[i] == 0) { noop = true; return SB_OK; }
+
+    // drop size-1 dims
+    int n = 0;
+    for (int i = 0; i < d.ndim; ++i) {
+        if (d.dims[i] == 1) continue;
+        c.dims[n] = d.dims[i];
+        for (int k = 0; k < c.nops; ++k) c.strides[k][n] = d.strides[k][i];
+        ++n;
+    }
+    if (n == 0) { // a single element
+        c.dims[0] = 1;
+        for (int k = 0; k < c.nops; ++k) c.strides[k][0] = 1;
+        n = 1;
+    }
+    c.ndim = n;
+
+    bool any_reduced = false;
+    for (int i = 0; i < n; ++i)
+        if (c.strides[0][i] == 0 && c.dims[i] > 1) any_reduced = true;
+    if (c.op == OP_NONE && any_reduced) {
+        // map mode with a zero output stride is "last write wins" in the reference's serial loop order
+        // (mapreduce.jl:312, :320-327): undefined for a parallel engine.
+        err = "map with a zero-stride (broadcast) output dim";
+        return SB_E_UNSUPPORTED;
+    }
+
+    if (c.op != OP_NONE && !any_reduced) {
+        // no reduced dim: out = op(initop(out), f(in...)) elementwise -> a map with the output as extra input
+        if (c.nops >= MAXO) { err = "too many operands for in-place op"; return SB_E_UNSUPPORTED; }
+        const int k = c.nops;
+        c.base[k] = c.base[0];
+        c.src[k] = 0;
+        c.dtype[k] = c.dtype[0];
+        c.conj[k] = c.conj[0];
+        for (int i = 0; i < n; ++i) c.strides[k][i] = c.strides[0][i];
+        c.nops = k + 1;
+        std::vector<Tok> t;
+        const Tok argout{TOK_ARG, k - 1, 0, 0};
+        switch (c.initop) {
+        case INIT_ZERO: t.push_back(Tok{TOK_CONST, 0, 0, 0}); break;
+        case INIT_CONST: t.push_back(Tok{TOK_CONST, 0, c.init_re, c.init_im}); break;
+        case INIT_SCALE:
+            t.push_back(Tok{TOK_CONST, 0, c.init_re, c.init_im});
+            t.push_back(argout);
+            t.push_back(Tok{TOK_CALL, FN_MUL, 0, 0});
+            break;
+        case INIT_CONJ:
+            t.push_back(argout);
+            t.push_back(Tok{TOK_CALL, FN_CONJ, 0, 0});
+            break;
+        default: t.push_back(argout); break;
+        }
+        if (c.ntok == 0) t.push_back(Tok{TOK_ARG, 0, 0, 0});
+        for (int i = 0; i < c.ntok; ++i) t.push_back(c.tok[i]);
+        const int fn = c.op == OP_ADD ? FN_ADD : c.op == OP_MUL ? FN_MUL : c.op == OP_MIN ? FN_MIN : FN_MAX;
+        t.push_back(Tok{TOK_CALL, fn, 0, 0});
+        if ((int)t.size() > MAXTOK) { err = "program too long"; return SB_E_UNSUPPORTED; }
+        c.ntok = (int)t.size();
+        for (int i = 0; i < c.ntok; ++i) c.tok[i] = t[i];
+        c.op = OP_NONE;
+        c.initop = INIT_NONE;
+        rc = check_program(c, err, depth);
+        if (rc != SB_OK) return rc;
+    }
+    if (depth > 4) { err = "program stack deeper than 4"; return SB_E_UNSUPPORTED; }
+    if (c.nops < 2) { // `out .= const`: give the functor a (never read) input so that a[0] exists
+        c.base[1] = c.base[0];
+        c.src[1] = 0;
+        c.dtype[1] = c.dtype[0];
+        c.conj[1] = 0;
+        for (int i = 0; i < n; ++i) c.strides[1][i] = c.strides[0][i];
+        c.nops = 2;
+    }
+
+    // sort: kept dims by |output stride|, then reduced dims by |first input stride| (zero strides last)
+    int idx[MAXD];
+    for (int i = 0; i < n; ++i) idx[i] = i;
+    auto key_in = [&](int i) {
+        int64_t s = iabs64(c.strides[1][i]);
+        return s == 0 ? INT64_MAX : s;
+    };
+    std::stable_sort(idx, idx + n, [&](int a, int b) {
+        const bool ra = c.strides[0][a] == 0, rb = c.strides[0][b] == 0;
+        if (ra != rb) return !ra; // kept first
+        if (!ra) {
+            const int64_t sa = iabs64(c.strides[0][a]), sb_ = iabs64(c.strides[0][b]);
+            if (sa != sb_) return sa < sb_;
+        }
+        return key_in(a) < key_in(b);
+    });
+    Canon s = c;
+    for (int i = 0; i < n; ++i) {
+        s.dims[i] = c.dims[idx[i]];
+        for (int k = 0; k < c.nops; ++k) s.strides[k][i] = c.strides[k][idx[i]];
+    }
+    // fuse neighbours that are contiguous in EVERY operand (the rule of mapreduce.jl:105-110, applied after
+    // sorting so that it finds every fusable pair -- SURVEY.md appendix E.5)
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+        bool merge = m > 0;
+        if (merge)
+            for (int k = 0; k < s.nops; ++k)
+                if (s.strides[k][i] != s.dims[m - 1] * s.strides[k][m - 1]) { merge = false; break; }
+        if (merge) {
+            s.dims[m - 1] *= s.dims[i];
+        } else {
+            s.dims[m] = s.dims[i];
+            for (int k = 0; k < s.nops; ++k) s.strides[k][m] = s.strides[k][i];
+            ++m;
+        }
+    }
+    s.ndim = m;
+    s.nkept = 0;
+    for (int i = 0; i < m; ++i)
+        if (s.strides[0][i] != 0 || s.op == OP_NONE) s.nkept++;
+    if (s.op != OP_NONE && m == 1 && s.dims[0] == 1) s.nkept = 1;
+    c = s;
+    return SB_OK;
+}
+
+// ---- order tables ---------------------------------------------------------------------------------------
+// slots: tile-dim indices (into tdim) in traversal order, fastest first
+void make_order(const int *slots, int n, const int *tbits, OrderTab &o)
+{
+    o.n = (uint8_t)n;
+    int sh = 0;
+    for (int i = 0; i < n; ++i) {
+        o.td[i] = (uint8_t)slots[i];
+        o.shift[i] = (uint8_t)sh;
+        o.bits[i] = (uint8_t)tbits[slots[i]];
+        sh += tbits[slots[i]];
+    }
+    for (int i = n; i < MAXTD; ++i) o.td[i] = o.shift[i] = o.bits[i] = 0;
+}
+bool same_order(const OrderTab &a, const OrderTab &b)
+{
+    if (a.n != b.n) return false;
+    for (int i = 0; i < a.n; ++i)
+        if (a.td[i] != b.td[i]) return false;
+    return true;
+}
+
+// order of the tile dims for operand strides `s` (by |stride| ascending, zero strides last)
+void operand_order(const Canon &c, int k, const int *tdim, int ntd, const int *tbits, OrderTab &o)
+{
+    int slots[MAXTD];
+    for (int i = 0; i < ntd; ++i) slots[i] = i;
+    std::stable_sort(slots, slots + ntd, [&](int a, int b) {
+        int64_t sa = iabs64(c.strides[k][tdim[a]]), sb_ = iabs64(c.strides[k][tdim[b]]);
+        if (sa == 0) sa = INT64_MAX;
+        if (sb_ == 0) sb_ = INT64_MAX;
+        return sa < sb_;
+    });
+    make_order(slots, ntd, tbits, o);
+}
+
+} // namespace
+
+// ---- shared-memory bank model -----------------------------------------------------------------------------
+// 32 banks x 4 B.  An access of `elem_bytes` per lane is served in groups of 128/elem_bytes lanes (whole
+// warp for 4 B, half-warps for 8 B, quarter-warps for 16 B); within a group the number of wavefronts is
+// the largest number of DISTINCT addresses that fall into one bank.
+int smem_wavefronts(const int32_t *elem_addr, int nlanes, int elem_bytes)
+{
+    const int words = elem_bytes / 4;
+    const int group = std::max(1, 32 / words);
+    int total = 0;
+    for (int g0 = 0; g0 < nlanes; g0 += group) {
+        int worst = 1;
+        for (int bank = 0; bank < 32; bank += words) {
+            int cnt = 0;
+            int32_t seen[32];
+            for (int l = g0; l < std::min(nlanes, g0 + group); ++l) {
+                const int b = (int)(((int64_t)elem_addr[l] * words) % 32);
+                if (b != bank) continue;
+                bool dup = false;
+                for (int q = 0; q < cnt; ++q)
+                    if (seen[q] == elem_addr[l]) dup = true;
+                if (!dup) seen[cnt++] = elem_addr[l];
+            }
+            worst = std::max(worst, cnt);
+        }
+        total += worst;
+    }
+    return total;
+}
+
+namespace {
+
+// choose padded shared-memory strides (in elements) for a staged operand.
+// own = its load order, out = output order; returns sigma per tile-dim slot and the buffer length.
+int32_t choose_smem_strides(const OrderTab &own, const OrderTab &out, int ntd, const int *tbits, int elem_bytes,
+                            int32_t *sigma)
+{
+    const int n = own.n;
+    int pads[MAXTD] = {0};
+    int bestpads[MAXTD] = {0};
+    long best_cost = -1;
+    int32_t best_len = 0;
+    const int maxpad = 8;
+    // iterate over all pad vectors (n-1 pads)
+    const int npad = std::max(0, n - 1);
+    long combos = 1;
+    for (int i = 0; i < npad; ++i) combos *= (maxpad + 1);
+    for (long cidx = 0; cidx < combos; ++cidx) {
+        long r = cidx;
+        for (int i = 0; i < npad; ++i) {
+            pads[i] = (int)(r % (maxpad + 1));
+            r /= (maxpad + 1);
+        }
+        int32_t sg[MAXTD] = {0};
+        int32_t cur = 1;
+        for (int i = 0; i < n; ++i) {
+            sg[own.td[i]] = cur;
+            cur = cur * (1 << own.bits[i]) + (i < npad ? pads[i] : 0);
+        }
+        int32_t len = 1;
+        for (int i = 0; i < n; ++i) len += ((1 << own.bits[i]) - 1) * sg[own.td[i]];
+        int32_t wa[32], ra[32];
+        for (int l = 0; l < 32; ++l) {
+            int32_t w = 0, rr = 0;
+            for (int i = 0; i < own.n; ++i) w += field_of(own, i, l) * sg[own.td[i]];
+            for (int i = 0; i < out.n; ++i) rr += field_of(out, i, l) * sg[out.td[i]];
+            wa[l] = w;
+            ra[l] = rr;
+        }
+        const long cost = smem_wavefronts(wa, 32, elem_bytes) + smem_wavefronts(ra, 32, elem_bytes);
+        if (best_cost < 0 || cost < best_cost || (cost == best_cost && len < best_len)) {
+            best_cost = cost;
+            best_len = len;
+            for (int i = 0; i < npad; ++i) bestpads[i] = pads[i];
+        }
+    }
+    int32_t cur = 1;
+    for (int i = 0; i < ntd; ++i) sigma[i] = 0;
+    for (int i = 0; i < n; ++i) {
+        sigma[own.td[i]] = cur;
+        cur = cur * (1 << own.bits[i]) + (i < npad ? bestpads[i] : 0);
+    }
+    (void)tbits;
+    return best_len;
+}
+
+int default_ept(int ct, int nin, int64_t needed)
+{
+    // value registers per thread ~ nin * EPT * words; instantiated: f32 {8,16}, f64 {8}, c32 {8}, c64 {4}
+    switch (ct) {
+    case F32: return (needed > THREADS * 8 && nin <= 4) ? 16 : 8;
+    case F64: return 8;
+    case C32: return 8;
+    default: return 4;
+    }
+}
+
+int template_nin(int recipe, int nin)
+{
+    switch (recipe) {
+    case RC_COPY: case RC_SCALE: case RC_ABS2: return 1;
+    case RC_ADD2: case RC_ADD2_DIV: case RC_ADD2_MUL: case RC_AXPY: case RC_AXPBY: return 2;
+    case RC_SUM3: return 3;
+    case RC_SUM4: return 4;
+    default: return nin <= 1 ? 1 : nin == 2 ? 2 : nin <= 4 ? 4 : MAXIN;
+    }
+}
+
+bool recipe_instantiated(int ct, int recipe, bool uniform, bool reduce)
+{
+    if (recipe == RC_INTERP) return true;
+    if (reduce) return uniform && (recipe == RC_COPY || recipe == RC_ABS2);
+    if (recipe == RC_COPY) return true; // uniform and converting copies
+    if (!uniform) return false;
+    if (ct == F32 || ct == F64) return true;
+    return recipe == RC_SCALE;
+}
+
+void fill_common_tables(const OrderTab &o, int ept, uint16_t (*jfield)[MAXTD])
+{
+    for (int j = 0; j < ept; ++j)
+        for (int i = 0; i < o.n; ++i) jfield[j][i] = (uint16_t)field_of(o, i, j * THREADS);
+}
+
+int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err)
+{
+    MapParams &P = plan.map;
+    std::memset(&P, 0, sizeof P);
+    const int n = c.ndim, nops = c.nops, nin = nops - 1;
+    const int esz = dtype_size(c.ct);
+    match_recipe(c, P.prog);
+    bool uniform = true;
+    for (int k = 0; k < nops; ++k)
+        if (c.dtype[k] != c.ct || c.conj[k]) uniform = false;
+    if (!recipe_instantiated(c.ct, P.prog.recipe, uniform, false)) P.prog.recipe = RC_INTERP;
+
+    // hot dims: the output's fastest dim and every input's fastest dim
+    int fastest[MAXO];
+    for (int k = 0; k < nops; ++k) {
+        int best = -1;
+        for (int i = 0; i < n; ++i) {
+            if (c.strides[k][i] == 0) continue;
+            if (best < 0 || iabs64(c.strides[k][i]) < iabs64(c.strides[k][best])) best = i;
+        }
+        fastest[k] = best; // -1: scalar broadcast
+    }
+    bool hot[MAXD] = {false};
+    hot[0] = true;
+    for (int k = 1; k < nops; ++k)
+        if (fastest[k] >= 0) hot[fastest[k]] = true;
+    int nhot = 0;
+    for (int i = 0; i < n; ++i) nhot += hot[i];
+
+    int cap[MAXD], tb[MAXD];
+    for (int i = 0; i < n; ++i) {
+        cap[i] = ilog2_ceil(c.dims[i]);
+        tb[i] = 0;
+    }
+    const int minrun_bits = ilog2_ceil(std::max(1, 32 / esz)); // 32-byte sector
+    int64_t needed = 1;
+    for (int i = 0; i < n; ++i)
+        if (hot[i]) needed <<= std::min(cap[i], minrun_bits);
+    const int ept = default_ept(c.ct, nin, needed);
+    const int ebits = LOG_THREADS + ilog2_ceil(ept);
+    int used = 0;
+    // phase 1: a sector-sized run along every hot dim
+    for (int i = 0; i < n && used < ebits; ++i)
+        if (hot[i]) {
+            const int b = std::min(std::min(cap[i], minrun_bits), ebits - used);
+            tb[i] = b;
+            used += b;
+        }
+    // phase 2: grow the hot dim with the shortest run (output dim first on ties)
+    while (used < ebits) {
+        int pick = -1;
+        for (int i = 0; i < n; ++i)
+            if (hot[i] && tb[i] < cap[i] && (pick < 0 || tb[i] < tb[pick])) pick = i;
+        if (pick < 0) break;
+        tb[pick]++;
+        used++;
+    }
+    // phase 3: other dims, in output order
+    auto ntile_dims = [&]() {
+        int q = 0;
+        for (int i = 0; i < n; ++i) q += tb[i] > 0;
+        return q;
+    };
+    for (int i = 0; i < n && used < ebits; ++i) {
+        if (hot[i] || cap[i] == 0) continue;
+        if (ntile_dims() >= MAXTD) break;
+        const int b = std::min(cap[i], ebits - used);
+        tb[i] = b;
+        used += b;
+    }
+    // phase 4: pad (elements beyond the array are masked)
+    if (used < ebits) {
+        tb[0] += ebits - used;
+        used = ebits;
+    }
+    if (ntile_dims() > MAXTD) { err = "too many tile dims"; return SB_E_UNSUPPORTED; }
+
+    // tile-dim slots in canonical (output) order
+    int tdim[MAXTD], tbits[MAXTD], ntd = 0;
+    for (int i = 0; i < n; ++i)
+        if (tb[i] > 0) {
+            tdim[ntd] = i;
+            tbits[ntd] = tb[i];
+            ++ntd;
+        }
+    P.ndim = n;
+    P.nops = nops;
+    P.ntd = ntd;
+    P.ept = ept;
+    P.uniform = uniform;
+    P.ntiles = 1;
+    for (int i = 0; i < n; ++i) {
+        P.dims[i] = c.dims[i];
+        P.tile_b[i] = 1 << tb[i];
+        const int64_t nt = (c.dims[i] + P.tile_b[i] - 1) / P.tile_b[i];
+        if (nt > 0x7fffffff) { err = "dim too large"; return SB_E_UNSUPPORTED; }
+        P.ntile[i] = (int32_t)nt;
+        P.ntiles *= nt;
+    }
+    for (int i = 0; i < ntd; ++i) P.tdim[i] = (uint8_t)tdim[i];
+    for (int k = 0; k < nops; ++k) {
+        P.base[k] = c.base[k];
+        P.dtype[k] = (uint8_t)c.dtype[k];
+        P.conj[k] = (uint8_t)c.conj[k];
+        for (int i = 0; i < n; ++i) P.strides[k][i] = c.strides[k][i];
+    }
+    // orders
+    int ident[MAXTD];
+    for (int i = 0; i < ntd; ++i) ident[i] = i;
+    make_order(ident, ntd, tbits, P.order[0]);
+    int32_t smem_elems = 0;
+    P.nstaged = 0;
+    for (int k = 1; k < nops; ++k) {
+        OrderTab own;
+        operand_order(c, k, tdim, ntd, tbits, own);
+        const bool bcast0 = ntd > 0 && c.strides[k][tdim[0]] == 0; // broadcast along the output's fastest tile dim
+        const bool direct = ntd == 0 || same_order(own, P.order[0]) || own.td[0] == P.order[0].td[0] || bcast0 ||
+                            fastest[k] < 0;
+        if (direct) {
+            P.staged[k] = 0;
+            P.order[k] = P.order[0];
+        } else {
+            P.staged[k] = 1;
+            P.order[k] = own;
+            P.nstaged++;
+        }
+    }
+    // functionals
+    for (int k = 0; k < nops; ++k) {
+        const OrderTab &o = P.order[k];
+        for (int i = 0; i < o.n; ++i) P.g_tstr[k][i] = c.strides[k][tdim[o.td[i]]];
+        for (int j = 0; j < ept; ++j) {
+            int64_t g = 0;
+            for (int i = 0; i < o.n; ++i) g += (int64_t)field_of(o, i, j * THREADS) * P.g_tstr[k][i];
+            P.g_joff[k][j] = g;
+        }
+        fill_common_tables(o, ept, P.jfield[k]);
+        if (k > 0 && P.staged[k]) {
+            int32_t sigma[MAXTD];
+            const int32_t len = choose_smem_strides(o, P.order[0], ntd, tbits, esz, sigma);
+            P.smem_off[k] = smem_elems;
+            smem_elems += (len + 3) & ~3;
+            const OrderTab &oo = P.order[0];
+            for (int i = 0; i < o.n; ++i) P.w_tstr[k][i] = sigma[o.td[i]];
+            for (int i = 0; i < oo.n; ++i) P.r_tstr[k][i] = sigma[oo.td[i]];
+            for (int j = 0; j < ept; ++j) {
+                int32_t w = 0, r = 0;
+                for (int i = 0; i < o.n; ++i) w += field_of(o, i, j * THREADS) * P.w_tstr[k][i];
+                for (int i = 0; i < oo.n; ++i) r += field_of(oo, i, j * THREADS) * P.r_tstr[k][i];
+                P.w_joff[k][j] = w;
+                P.r_joff[k][j] = r;
+            }
+        }
+    }
+    plan.kind = PLAN_MAP;
+    for (int k = 0; k < MAXO; ++k) plan.base_src[k] = c.src[k];
+    plan.family = "map_tile";
+    plan.key = KernelKey{c.ct, P.prog.recipe, template_nin(P.prog.recipe, nin), ept, uniform ? 1 : 0};
+    plan.smem_bytes = (int64_t)smem_elems * esz;
+    if (plan.smem_bytes > 200 * 1024) { err = "staging buffers exceed shared memory"; return SB_E_UNSUPPORTED; }
+    plan.grid = std::min<int64_t>(P.ntiles, (int64_t)dev.sm_count * dev.ctas_per_sm);
+    plan.elements = 1;
+    for (int i = 0; i < n; ++i) plan.elements *= c.dims[i];
+    return SB_OK;
+}
+
+int plan_reduce(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err)
+{
+    ReduceParams &P = plan.red;
+    std::memset(&P, 0, sizeof P);
+    const int n = c.ndim, nops = c.nops, nin = nops - 1;
+    const int esz = dtype_size(c.ct);
+    match_recipe(c, P.prog);
+    bool uniform = true;
+    for (int k = 0; k < nops; ++k)
+        if (c.dtype[k] != c.ct || c.conj[k]) uniform = false;
+    if (!recipe_instantiated(c.ct, P.prog.recipe, uniform, true)) P.prog.recipe = RC_INTERP;
+    if (nin > 3) { err = "reduction over more than 3 inputs"; return SB_E_UNSUPPORTED; }
+
+    const int ept = (c.ct == C64) ? 4 : 8;
+    const int ebits = LOG_THREADS + ilog2_ceil(ept);
+    // dims in the first input's stride order
+    int ord[MAXD];
+    for (int i = 0; i < n; ++i) ord[i] = i;
+    std::stable_sort(ord, ord + n, [&](int a, int b) {
+        int64_t sa = iabs64(c.strides[1][a]), sb_ = iabs64(c.strides[1][b]);
+        if (sa == 0) sa = INT64_MAX;
+        if (sb_ == 0) sb_ = INT64_MAX;
+        return sa < sb_;
+    });
+    int tb[MAXD] = {0};
+    int used = 0, ntdims = 0;
+    for (int q = 0; q < n && used < ebits && ntdims < MAXTD; ++q) {
+        const int i = ord[q];
+        const int b = std::min(ilog2_ceil(c.dims[i]), ebits - used);
+        if (b == 0) continue;
+        tb[i] = b;
+        used += b;
+        ntdims++;
+    }
+    if (used < ebits) { // pad along the fastest dim (masked)
+        if (ntdims == 0) ntdims = 1;
+        tb[ord[0]] += ebits - used;
+        used = ebits;
+    }
+    int tdim[MAXTD], tbits[MAXTD], ntd = 0;
+    for (int i = 0; i < n; ++i)
+        if (tb[i] > 0) {
+            tdim[ntd] = i;
+            tbits[ntd] = tb[i];
+            ++ntd;
+        }
+    P.ndim = n;
+    P.nops = nops;
+    P.ntd = ntd;
+    P.nkept = c.nkept;
+    P.ept = ept;
+    P.uniform = uniform;
+    P.op = c.op;
+    P.initop = c.initop;
+    P.init_re = c.init_re;
+    P.init_im = c.init_im;
+    P.nouttiles = 1;
+    P.nrsteps = 1;
+    for (int i = 0; i < n; ++i) {
+        P.dims[i] = c.dims[i];
+        P.tile_b[i] = 1 << tb[i];
+        const int64_t nt = (c.dims[i] + P.tile_b[i] - 1) / P.tile_b[i];
+        if (nt > 0x7fffffff) { err = "dim too large"; return SB_E_UNSUPPORTED; }
+        P.ntile[i] = (int32_t)nt;
+        if (i < c.nkept) P.nouttiles *= nt;
+        else P.nrsteps *= nt;
+    }
+    for (int i = 0; i < ntd; ++i) P.tdim[i] = (uint8_t)tdim[i];
+    for (int k = 0; k < nops; ++k) {
+        P.base[k] = c.base[k];
+        P.dtype[k] = (uint8_t)c.dtype[k];
+        P.conj[k] = (uint8_t)c.conj[k];
+        for (int i = 0; i < n; ++i) P.strides[k][i] = c.strides[k][i];
+    }
+    operand_order(c, 1, tdim, ntd, tbits, P.order);
+    for (int k = 1; k < nops; ++k) {
+        for (int i = 0; i < P.order.n; ++i) P.g_tstr[k][i] = c.strides[k][tdim[P.order.td[i]]];
+        for (int j = 0; j < ept; ++j) {
+            int64_t g = 0;
+            for (int i = 0; i < P.order.n; ++i) g += (int64_t)field_of(P.order, i, j * THREADS) * P.g_tstr[k][i];
+            P.g_joff[k][j] = g;
+        }
+    }
+    fill_common_tables(P.order, ept, P.jfield);
+    // in-CTA combine layout
+    int kslots[MAXTD], nk = 0;
+    int32_t kdense[MAXTD] = {0}, rdense[MAXTD] = {0};
+    int32_t nout = 1, nred = 1;
+    for (int i = 0; i < ntd; ++i)
+        if (tdim[i] < c.nkept) {
+            kslots[nk++] = i;
+            kdense[i] = nout;
+            nout <<= tbits[i];
+        }
+    for (int q = 0; q < P.order.n; ++q) {
+        const int i = P.order.td[q];
+        if (tdim[i] >= c.nkept) {
+            rdense[i] = nred;
+            nred <<= tbits[i];
+        }
+    }
+    P.nout_tile = nout;
+    P.nred_tile = nred;
+    P.warp_per_output = nred >= 32 ? 1 : 0;
+    make_order(kslots, nk, tbits, P.kept_order);
+    for (int q = 0; q < P.order.n; ++q) {
+        const int i = P.order.td[q];
+        if (tdim[i] < c.nkept) P.s_tstr[q] = kdense[i] * (P.warp_per_output ? nred : 1);
+        else P.s_tstr[q] = rdense[i] * (P.warp_per_output ? 1 : nout);
+    }
+    for (int j = 0; j < ept; ++j) {
+        int32_t s = 0;
+        for (int q = 0; q < P.order.n; ++q) s += field_of(P.order, q, j * THREADS) * P.s_tstr[q];
+        P.s_joff[j] = s;
+    }
+    // splits of the reduced index space
+    const int64_t target = (int64_t)dev.sm_count * dev.ctas_per_sm;
+    int64_t nsplit = 1;
+    if (P.nouttiles < target) nsplit = std::min<int64_t>(P.nrsteps, (target + P.nouttiles - 1) / P.nouttiles);
+    P.steps_per_split = (P.nrsteps + nsplit - 1) / nsplit;
+    nsplit = (P.nrsteps + P.steps_per_split - 1) / P.steps_per_split;
+    if (nsplit > 0x7fffffff) { err = "too many splits"; return SB_E_UNSUPPORTED; }
+    P.nsplit = (int32_t)nsplit;
+    plan.kind = PLAN_REDUCE;
+    for (int k = 0; k < MAXO; ++k) plan.base_src[k] = c.src[k];
+    plan.family = "reduce_tile";
+    plan.key = KernelKey{c.ct, P.prog.recipe, P.prog.recipe == RC_INTERP ? (nin <= 1 ? 1 : nin == 2 ? 2 : 3) : 1, ept,
+                         uniform ? 1 : 0};
+    plan.smem_bytes = (int64_t)THREADS * ept * esz;
+    plan.grid = P.nouttiles * nsplit;
+    plan.scratch_bytes = nsplit > 1 ? nsplit * P.nouttiles * (int64_t)nout * esz : 0;
+    plan.finalize_threads = nsplit > 1 ? P.nouttiles * (int64_t)nout : 0;
+    plan.elements = 1;
+    for (int i = 0; i < n; ++i) plan.elements *= c.dims[i];
+    if (plan.grid > 0x7fffffff) { err = "grid too large"; return SB_E_UNSUPPORTED; }
+    return SB_OK;
+}
+
+} // namespace
+
+// _mapreducedim! with a zero-size dim applies initop to a non-empty output (reference mapreduce.jl:88-91)
+bool empty_initop_desc(const sb_desc &D, sb_desc &E)
+{
+    bool anyzero = false;
+    for (int i = 0; i < D.ndim; ++i)
+        if (D.dims[i] == 0) anyzero = true;
+    if (!anyzero || D.op == SB_OP_NONE || D.initop == SB_INIT_NONE || D.initop == SB_INIT_IDENTITY) return false;
+    std::memset(&E, 0, sizeof E);
+    for (int i = 0; i < D.ndim; ++i) {
+        if (D.strides[0][i] == 0 && D.dims[i] != 1) continue;
+        if (D.dims[i] == 0) return false;
+        E.dims[E.ndim] = D.dims[i];
+        E.strides[0][E.ndim] = D.strides[0][i];
+        E.strides[1][E.ndim] = D.strides[0][i];
+        E.ndim++;
+    }
+    E.nops = 2;
+    E.base[0] = E.base[1] = D.base[0];
+    E.dtype[0] = E.dtype[1] = D.dtype[0];
+    E.conj[0] = E.conj[1] = D.conj[0];
+    E.op = SB_OP_NONE;
+    switch (D.initop) {
+    case SB_INIT_ZERO: E.ntok = 1; E.prog[0] = sb_tok{SB_TOK_CONST, 0, 0.0, 0.0}; break;
+    case SB_INIT_CONST: E.ntok = 1; E.prog[0] = sb_tok{SB_TOK_CONST, 0, D.init_re, D.init_im}; break;
+    case SB_INIT_SCALE:
+        E.ntok = 3;
+        E.prog[0] = sb_tok{SB_TOK_CONST, 0, D.init_re, D.init_im};
+        E.prog[1] = sb_tok{SB_TOK_ARG, 0, 0, 0};
+        E.prog[2] = sb_tok{SB_TOK_CALL, SB_FN_MUL, 0, 0};
+        break;
+    default:
+        E.ntok = 2;
+        E.prog[0] = sb_tok{SB_TOK_ARG, 0, 0, 0};
+        E.prog[1] = sb_tok{SB_TOK_CALL, SB_FN_CONJ, 0, 0};
+        break;
+    }
+    return true;
+}
+
+int build_plan(const sb_desc &d, const DeviceInfo &dev, Plan &plan, std::string &err)
+{
+    sb_desc E;
+    if (empty_initop_desc(d, E)) { // map!(initop, out, out) over the kept dims
+        const int rc = build_plan(E, dev, plan, err);
+        for (int k = 0; k < MAXO; ++k) plan.base_src[k] = 0;
+        return rc;
+    }
+    Canon c;
+    bool noop = false;
+    int rc = canonicalise(d, c, noop, err);
+    if (rc != SB_OK) return rc;
+    if (noop) {
+        plan.kind = PLAN_NOOP;
+        plan.family = "noop";
+        return SB_OK;
+    }
+    if (c.op == OP_NONE) return plan_map(c, dev, plan, err);
+    return plan_reduce(c, dev, plan, err);
+}
+
+std::string describe_plan(const Plan &p)
+{
+    std::ostringstream os;
+    os << "{\"family\":\"" << p.family << "\"";
+    if (p.kind == PLAN_NOOP) {
+        os << "}";
+        return os.str();
+    }
+    static const char *ctn[] = {"f32", "f64", "c32", "c64"};
+    static const char *rcn[] = {"interp", "copy", "scale", "add2", "add2_div", "add2_mul", "sum3", "sum4", "axpy", "axpby", "abs2"};
+    os << ",\"ct\":\"" << ctn[p.key.ct] << "\",\"recipe\":\"" << rcn[p.key.recipe] << "\",\"nin_t\":" << p.key.nin
+       << ",\"ept\":" << p.key.ept << ",\"uniform\":" << p.key.uniform << ",\"grid\":" << p.grid
+       << ",\"smem_bytes\":" << p.smem_bytes << ",\"elements\":" << p.elements;
+    auto arr64 = [&](const char *name, const int64_t *v, int n) {
+        os << ",\"" << name << "\":[";
+        for (int i = 0; i < n; ++i) os << (i ? "," : "") << v[i];
+        os << "]";
+    };
+    auto arr32 = [&](const char *name, const int32_t *v, int n) {
+        os << ",\"" << name << "\":[";
+        for (int i = 0; i < n; ++i) os << (i ? "," : "") << v[i];
+        os << "]";
+    };
+    if (p.kind == PLAN_MAP) {
+        const MapParams &P = p.map;
+        arr64("dims", P.dims, P.ndim);
+        arr32("tile", P.tile_b, P.ndim);
+        os << ",\"ntiles\":" << P.ntiles << ",\"nstaged\":" << P.nstaged << ",\"staged\":[";
+        for (int k = 0; k < P.nops; ++k) os << (k ? "," : "") << (int)P.staged[k];
+        os << "],\"strides\":[";
+        for (int k = 0; k < P.nops; ++k) {
+            os << (k ? "," : "") << "[";
+            for (int i = 0; i < P.ndim; ++i) os << (i ? "," : "") << P.strides[k][i];
+            os << "]";
+        }
+        os << "]";
+    } else {
+        const ReduceParams &P = p.red;
+        arr64("dims", P.dims, P.ndim);
+        arr32("tile", P.tile_b, P.ndim);
+        os << ",\"nkept\":" << P.nkept << ",\"nouttiles\":" << P.nouttiles << ",\"nrsteps\":" << P.nrsteps
+           << ",\"nsplit\":" << P.nsplit << ",\"steps_per_split\":" << P.steps_per_split
+           << ",\"nout_tile\":" << P.nout_tile << ",\"nred_tile\":" << P.nred_tile
+           << ",\"warp_per_output\":" << P.warp_per_output << ",\"scratch_bytes\":" << p.scratch_bytes;
+    }
+    os << "}";
+    return os.str();
+}
+
+} // namespace sb

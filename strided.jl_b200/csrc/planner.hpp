@@ -1,0 +1,58 @@
+// planner.hpp -- host planner: sb_desc -> canonical problem -> tile plan (MapParams / ReduceParams).
+//
+// GPU counterpart of the reference planner `_mapreduce_fuse!` / `_mapreduce_order!` / `_computeblocks`
+// (src/mapreduce.jl:98-139, 463-520).  Only two ideas carry over: fusing dims that are contiguous in every
+// operand (:103-115) and ranking dims by stride order (:119-139).  The cache-line block model (:503-520) and
+// the task bisection (:195-227) are CPU-specific and are replaced by shared-memory tiles and a CTA grid.
+#pragma once
+#include "common.hpp"
+#include "../../include/strided_b200.h"
+#include <string>
+
+namespace sb {
+
+enum PlanKind : int { PLAN_NOOP = 0, PLAN_MAP = 1, PLAN_REDUCE = 2 };
+
+struct DeviceInfo {
+    int sm_count = 148;        // B200
+    int ctas_per_sm = 4;       // resident CTAs of THREADS threads assumed for grid sizing
+};
+
+struct KernelKey {
+    int ct;      // compute dtype (DType)
+    int recipe;  // Recipe
+    int nin;     // template NIN
+    int ept;     // template EPT
+    int uniform; // template UNIFORM
+};
+
+struct Plan {
+    int kind = PLAN_NOOP;
+    KernelKey key{};
+    MapParams map{};
+    ReduceParams red{};
+    int64_t grid = 0;
+    int64_t smem_bytes = 0;
+    int64_t scratch_bytes = 0;      // reduce partials
+    int64_t finalize_threads = 0;   // > 0: launch reduce_finalize
+    int64_t elements = 0;           // size of the canonical index space
+    std::string family;             // "map_tile" | "reduce_tile" | "noop"
+    int base_src[MAXO] = {0, 1, 2, 3, 4, 5, 6, 7}; // canonical operand k reads sb_desc::base[base_src[k]]
+    // optional alias-aware tile order (host copy; uploaded by the ctx)
+    std::string note;
+};
+
+// Returns sb_status.  `err` receives a message on failure.
+int build_plan(const sb_desc &d, const DeviceInfo &dev, Plan &plan, std::string &err);
+
+// `_mapreducedim!` with a zero-size dim applies initop to a non-empty output (reference mapreduce.jl:88-91):
+// rewrites D into the equivalent `map!(initop, out, out)`; false when nothing has to be done.
+bool empty_initop_desc(const sb_desc &D, sb_desc &E);
+
+// one-line JSON (sb_plan_describe)
+std::string describe_plan(const Plan &plan);
+
+// shared-memory bank model used by the padding search (exposed for tests)
+int smem_wavefronts(const int32_t *elem_addr, int nlanes, int elem_bytes);
+
+} // namespace sb

@@ -1,0 +1,157 @@
+// emul.cpp -- TEST INFRASTRUCTURE ONLY: CPU thread-grid emulation of the CUDA tile kernels.
+//
+// There is no GPU in the build container, so the index machinery (planner tables, per-thread offset
+// functionals, staging-buffer slots, edge masks, split reductions) is verified here by running the SAME
+// host/device-neutral kernel bodies (csrc/map_tile.hpp, csrc/reduce_tile.hpp) for every (block, thread) of
+// the launch on the CPU.  This library is built and loaded only by tests/ (CPU suite); the product library
+// contains no CPU execution path and never links this file.
+#include "../../strided.jl_b200/csrc/map_tile.hpp"
+#include "../../strided.jl_b200/csrc/reduce_tile.hpp"
+#include "../../strided.jl_b200/csrc/planner.hpp"
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace sb;
+
+static std::string g_err;
+
+template <class CT, int RC, int NIN, int EPT, bool U> static void run_map(const Plan &plan, int grid)
+{
+    const MapParams &P = plan.map;
+    std::vector<CT> smem((size_t)plan.smem_bytes / sizeof(CT) + 16);
+    std::vector<MapThread<NIN + 1>> th(THREADS);
+    for (int t = 0; t < THREADS; ++t) map_thread_init<NIN + 1>(P, t, th[t]);
+    using Regs = CT[NIN][EPT];
+    std::vector<char> regbuf(sizeof(Regs) * THREADS);
+    Regs *v = reinterpret_cast<Regs *>(regbuf.data());
+    for (int b = 0; b < grid; ++b)
+        for (int64_t pos = b; pos < P.ntiles; pos += grid) {
+            MapTile tl;
+            map_tile_init(P, pos, tl);
+            for (int t = 0; t < THREADS; ++t) map_phase1<CT, NIN, EPT, U>(P, th[t], tl, t, v[t], smem.data());
+            for (int t = 0; t < THREADS; ++t) map_phase2<CT, RC, NIN, EPT, U>(P, th[t], tl, t, v[t], smem.data());
+        }
+}
+
+template <class AT, int RC, int NIN, int EPT, bool U> static void run_reduce(const Plan &plan)
+{
+    const ReduceParams &P = plan.red;
+    std::vector<AT> smem((size_t)THREADS * EPT);
+    for (int64_t bid = 0; bid < plan.grid; ++bid) {
+        for (int t = 0; t < THREADS; ++t) red_accumulate<AT, RC, NIN, EPT, U>(P, bid, t, smem.data());
+        if (P.warp_per_output) {
+            for (int warp = 0; warp < THREADS / 32; ++warp)
+                for (int o = warp; o < P.nout_tile; o += THREADS / 32) {
+                    AT p[32];
+                    for (int lane = 0; lane < 32; ++lane) p[lane] = red_lane_partial<AT>(P, smem.data(), o, lane);
+                    for (int m = 16; m >= 1; m >>= 1) { // butterfly, as __shfl_xor_sync
+                        AT q[32];
+                        for (int lane = 0; lane < 32; ++lane) q[lane] = red_apply<AT>(P.op, p[lane], p[lane ^ m]);
+                        std::memcpy(p, q, sizeof p);
+                    }
+                    red_finish<AT, U>(P, bid, o, p[0]);
+                }
+        } else {
+            for (int t = 0; t < THREADS; ++t)
+                for (int o = t; o < P.nout_tile; o += THREADS) red_finish<AT, U>(P, bid, o, red_thread_partial<AT>(P, smem.data(), o));
+        }
+    }
+    if (plan.finalize_threads > 0) {
+        const int64_t g = (plan.finalize_threads + THREADS - 1) / THREADS;
+        for (int64_t idx = 0; idx < g * THREADS; ++idx) red_finalize<AT, U>(P, idx);
+    }
+}
+
+// dispatch over the instantiated tuples (mirror of csrc/kernels_*.cu)
+template <class CT, bool U> static bool map_dispatch_interp(const Plan &plan, int grid)
+{
+    const int nin = plan.key.nin, ept = plan.key.ept;
+#define TRY(N, E)                                                                                                    \
+    if (nin == N && ept == E) {                                                                                      \
+        run_map<CT, RC_INTERP, N, E, U>(plan, grid);                                                                 \
+        return true;                                                                                                 \
+    }
+    TRY(1, 4) TRY(2, 4) TRY(4, 4) TRY(7, 4) TRY(1, 8) TRY(2, 8) TRY(4, 8) TRY(7, 8) TRY(1, 16) TRY(2, 16) TRY(4, 16) TRY(7, 16)
+#undef TRY
+    return false;
+}
+
+template <class CT> static bool map_dispatch(const Plan &plan, int grid)
+{
+    const KernelKey &k = plan.key;
+    if (k.recipe == RC_INTERP) return k.uniform ? map_dispatch_interp<CT, true>(plan, grid) : map_dispatch_interp<CT, false>(plan, grid);
+#define TRYR(R, N)                                                                                                   \
+    if (k.recipe == R && k.nin == N && k.uniform) {                                                                  \
+        if (k.ept == 4) { run_map<CT, R, N, 4, true>(plan, grid); return true; }                                     \
+        if (k.ept == 8) { run_map<CT, R, N, 8, true>(plan, grid); return true; }                                     \
+        if (k.ept == 16) { run_map<CT, R, N, 16, true>(plan, grid); return true; }                                   \
+    }
+    TRYR(RC_COPY, 1) TRYR(RC_SCALE, 1) TRYR(RC_ABS2, 1) TRYR(RC_ADD2, 2) TRYR(RC_ADD2_DIV, 2) TRYR(RC_ADD2_MUL, 2)
+    TRYR(RC_AXPY, 2) TRYR(RC_AXPBY, 2) TRYR(RC_SUM3, 3) TRYR(RC_SUM4, 4)
+#undef TRYR
+    if (k.recipe == RC_COPY && k.nin == 1 && !k.uniform) {
+        if (k.ept == 4) { run_map<CT, RC_COPY, 1, 4, false>(plan, grid); return true; }
+        if (k.ept == 8) { run_map<CT, RC_COPY, 1, 8, false>(plan, grid); return true; }
+        if (k.ept == 16) { run_map<CT, RC_COPY, 1, 16, false>(plan, grid); return true; }
+    }
+    return false;
+}
+
+template <class AT, int EPT> static bool red_dispatch(const Plan &plan)
+{
+    const KernelKey &k = plan.key;
+    if (k.ept != EPT) return false;
+    if (k.recipe == RC_COPY && k.uniform) { run_reduce<AT, RC_COPY, 1, EPT, true>(plan); return true; }
+    if (k.recipe == RC_ABS2 && k.uniform) { run_reduce<AT, RC_ABS2, 1, EPT, true>(plan); return true; }
+    if (k.recipe == RC_INTERP) {
+#define TRY(N)                                                                                                       \
+    if (k.nin == N) {                                                                                                \
+        if (k.uniform) run_reduce<AT, RC_INTERP, N, EPT, true>(plan);                                                \
+        else run_reduce<AT, RC_INTERP, N, EPT, false>(plan);                                                         \
+        return true;                                                                                                 \
+    }
+        TRY(1) TRY(2) TRY(3)
+#undef TRY
+    }
+    return false;
+}
+
+extern "C" const char *emul_last_error(void) { return g_err.c_str(); }
+
+// Runs `desc` (HOST pointers) exactly as the CUDA launch would be organised.  `grid_limit` > 0 overrides the
+// persistent-grid size of the map kernel (to exercise the tile loop with few CTAs).
+extern "C" int emul_mapreduce(const sb_desc *desc, int grid_limit)
+{
+    Plan plan;
+    DeviceInfo dev;
+    int rc = build_plan(*desc, dev, plan, g_err);
+    if (rc != SB_OK) return rc;
+    if (plan.kind == PLAN_NOOP) return SB_OK;
+    bool ok = false;
+    if (plan.kind == PLAN_MAP) {
+        int grid = (int)plan.grid;
+        if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;
+        switch (plan.key.ct) {
+        case F32: ok = map_dispatch<float>(plan, grid); break;
+        case F64: ok = map_dispatch<double>(plan, grid); break;
+        case C32: ok = map_dispatch<cx<float>>(plan, grid); break;
+        default: ok = map_dispatch<cx<double>>(plan, grid); break;
+        }
+    } else {
+        std::vector<unsigned char> scratch((size_t)plan.scratch_bytes + 64);
+        plan.red.scratch = scratch.data();
+        switch (plan.key.ct) {
+        case F32: ok = red_dispatch<float, 8>(plan); break;
+        case F64: ok = red_dispatch<double, 8>(plan); break;
+        case C32: ok = red_dispatch<cx<float>, 8>(plan); break;
+        default: ok = red_dispatch<cx<double>, 4>(plan); break;
+        }
+    }
+    if (!ok) {
+        g_err = "emul: no instantiation for this kernel key";
+        return SB_E_UNSUPPORTED;
+    }
+    return SB_OK;
+}

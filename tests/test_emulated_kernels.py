@@ -1,0 +1,23 @@
+"""CPU suite: the CUDA kernel BODIES (csrc/map_tile.hpp, csrc/reduce_tile.hpp) and the C++ planner, executed
+for every (block, thread) on the CPU by tests/emul/.  This checks the index machinery -- per-operand load
+orders, offset functionals, staging slots, edge masks, split reductions -- without a GPU.  It is not a
+product path: the emulator library is built only here."""
+import numpy as np
+import pytest
+
+import cases
+from helpers import case_c1, case_c2, case_c3, case_c4, case_c5
+
+
+@pytest.mark.parametrize("case", cases.all_cases(0.3), ids=lambda c: c.name)
+def test_emulated_kernel_matches_semantic_oracle(case):
+    want = case.expected()
+    case.assert_close(case.run_emul(), want)
+    case.assert_close(case.run_emul(grid_limit=2), want)  # few persistent CTAs: exercises the tile loop
+
+
+def test_emulated_baseline_configs():
+    for c in (case_c1(150), case_c2(260), case_c3(16), case_c4(16)):
+        c.assert_close(c.run_emul(), exact=True)
+    c5 = case_c5(8, 96)
+    c5.assert_close(c5.run_emul())
