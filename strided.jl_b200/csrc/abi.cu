@@ -50,6 +50,11 @@ const ReduceEntry *find_reduce_kernel(const KernelKey &k)
 
 static thread_local std::string g_tls_err;
 
+struct CachedPlan {
+    Plan plan;
+    void *dev_order = nullptr;
+};
+
 struct sb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -67,8 +72,16 @@ struct sb_ctx {
     // host staging pool (sb_mapreduce_host)
     void *stage = nullptr;
     size_t stage_bytes = 0;
-    std::unordered_map<std::string, Plan> plans;
+    std::unordered_map<std::string, CachedPlan> plans;
 };
+
+static void clear_plans(sb_ctx *ctx)
+{
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->plans)
+        if (kv.second.dev_order) cudaFree(kv.second.dev_order);
+    ctx->plans.clear();
+}
 
 static int set_err(sb_ctx *ctx, int code, const std::string &msg)
 {
@@ -134,6 +147,7 @@ int sb_ctx_destroy(sb_ctx *ctx)
     if (!ctx) return SB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    clear_plans(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -252,7 +266,13 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
     // plan cache: everything but the base pointers (the reference re-plans on every call; config 3 is ~2 us
     // of device work, so planning must not be on the critical path)
     sb_desc keyd = desc;
-    for (int k = 0; k < SB_MAX_OPS; ++k) keyd.base[k] = nullptr;
+    for (int k = 0; k < SB_MAX_OPS; ++k) { // keep only the ALIAS pattern of the bases (which operands share a parent pointer)
+        uintptr_t first = 0;
+        if (k < desc.nops)
+            for (int q = k; q >= 0; --q)
+                if (desc.base[q] == desc.base[k]) first = (uintptr_t)q + 1;
+        keyd.base[k] = (void *)first;
+    }
     for (int i = keyd.ndim; i < SB_MAX_DIMS; ++i) keyd.dims[i] = 0;
     for (int k = 0; k < SB_MAX_OPS; ++k)
         for (int i = 0; i < SB_MAX_DIMS; ++i)
@@ -268,12 +288,25 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
         rc = build_plan(desc, ctx->dev, fresh, err);
         if (rc != SB_OK) return set_err(ctx, rc, err);
         ctx->stats.plans_built++;
-        if (ctx->plans.size() > 4096) ctx->plans.clear();
-        hit = ctx->plans.emplace(std::move(key), std::move(fresh)).first;
+        if (ctx->plans.size() > 4096) clear_plans(ctx);
+        CachedPlan cp;
+        cp.plan = std::move(fresh);
+        if (!cp.plan.tile_order.empty()) { // alias-aware launch order: lives on the device with the plan
+            cudaSetDevice(ctx->device);
+            const size_t bytes = cp.plan.tile_order.size() * sizeof(int32_t);
+            cudaError_t e = cudaMalloc(&cp.dev_order, bytes);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(cp.dev_order, cp.plan.tile_order.data(), bytes, cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "tile order upload");
+            cp.plan.tile_order.clear();
+            cp.plan.tile_order.shrink_to_fit();
+        }
+        hit = ctx->plans.emplace(std::move(key), std::move(cp)).first;
     } else {
         ctx->stats.plans_cached++;
     }
-    Plan plan = hit->second; // copy: bases are bound per call
+    Plan plan = hit->second.plan; // copy: bases are bound per call
+    plan.map.tile_order = (const int32_t *)hit->second.dev_order;
     for (int k = 0; k < MAXO; ++k) {
         plan.map.base[k] = (unsigned char *)desc.base[plan.base_src[k] < desc.nops ? plan.base_src[k] : 0];
         plan.red.base[k] = plan.map.base[k];
@@ -311,7 +344,7 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
         if (e != cudaSuccess) return cuda_fail(ctx, e, "reduce_tile launch");
         ctx->stats.launches++;
         if (plan.finalize_threads > 0) {
-            const int64_t g = (plan.finalize_threads + THREADS - 1) / THREADS;
+            const int64_t g = (plan.finalize_threads + (THREADS / 32) - 1) / (THREADS / 32); // one warp per output
             e = k->finalize(plan.red, (int)g, ctx->stream);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "reduce_finalize launch");
             ctx->stats.launches++;

@@ -86,6 +86,37 @@ struct OrderTab {
     uint8_t bits[MAXTD];
 };
 
+// ---- division by a launch-time constant (tile decode) ---------------------------------------------------
+// q = x / n for x < 2^31 with one mul.hi + shift (round-up magic number, Granlund & Montgomery).  Replaces
+// the 64-bit div/mod chain that dominated the first profile (profiles/r01_v0_*: ~79 instr/element).
+struct FastDiv {
+    uint32_t mul, shr, n;
+};
+SB_HD uint32_t sb_umulhi(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+SB_HD void fast_divmod(const FastDiv &f, uint32_t x, uint32_t &q, uint32_t &r)
+{
+    q = (f.n == 1u) ? x : (sb_umulhi(x, f.mul) >> f.shr);
+    r = x - q * f.n;
+}
+inline FastDiv make_fastdiv(uint32_t n)
+{
+    FastDiv f{0u, 0u, n};
+    if (n <= 1u) return f;
+    uint32_t lg = 0;
+    while ((1ull << lg) < (uint64_t)n) ++lg;
+    const uint32_t p = 31u + lg;
+    f.mul = (uint32_t)(((1ull << p) + n - 1ull) / n);
+    f.shr = p - 32u;
+    return f;
+}
+
 // ---- map plan (kernel parameter block) -------------------------------------------------------------
 struct MapParams {
     int32_t ndim;  // canonical dims (size-1 dropped, fused, sorted by |output stride|)
@@ -95,6 +126,9 @@ struct MapParams {
     int64_t dims[MAXD];
     int32_t tile_b[MAXD]; // tile extent per canonical dim (1 for grid-only dims)
     int32_t ntile[MAXD];  // ceil(dims/tile_b)
+    int32_t nfull[MAXD];  // dims/tile_b: tile coordinate c is an interior (unmasked) tile iff c < nfull
+    FastDiv tdiv[MAXD];   // division by ntile[d]
+    int64_t tstep[MAXO][MAXD]; // BYTES per tile step along d: tile_b[d] * strides[k][d] * sizeof(elem k)
     uint8_t tdim[MAXTD];  // tile-dim slot -> canonical dim
     int64_t ntiles;
     const int32_t *tile_order; // optional device table: launch position -> tile id (alias-aware order)
@@ -104,13 +138,14 @@ struct MapParams {
     uint8_t conj[MAXO];
     uint8_t staged[MAXO];  // 1: loaded in own order, transposed through shared memory
     OrderTab order[MAXO];  // order[0] = output order; order[k] = load order of operand k
-    int64_t g_tstr[MAXO][MAXTD]; // global element stride per order slot (for toff)
+    // all address functionals are in BYTES
+    int64_t g_tstr[MAXO][MAXTD]; // global byte stride per order slot (for toff)
     int64_t g_joff[MAXO][MAXEPT];
-    int32_t w_tstr[MAXO][MAXTD]; // shared-memory slot stride per OWN-order slot (staged operands)
+    int32_t w_tstr[MAXO][MAXTD]; // shared-memory byte stride per OWN-order slot (staged operands)
     int32_t w_joff[MAXO][MAXEPT];
-    int32_t r_tstr[MAXO][MAXTD]; // shared-memory slot stride per OUTPUT-order slot
+    int32_t r_tstr[MAXO][MAXTD]; // shared-memory byte stride per OUTPUT-order slot
     int32_t r_joff[MAXO][MAXEPT];
-    int32_t smem_off[MAXO];      // element offset of the operand's staging buffer (units of CT)
+    int32_t smem_off[MAXO];      // byte offset of the operand's staging buffer (elements stored as CT)
     uint16_t jfield[MAXO][MAXEPT][MAXTD]; // coordinate bits contributed by j, per order slot
     int32_t ept;
     int32_t uniform; // all dtypes == compute type and no conj flags
@@ -124,7 +159,11 @@ struct ReduceParams {
     int64_t dims[MAXD];
     int32_t tile_b[MAXD];
     int32_t ntile[MAXD];
+    int32_t nfull[MAXD];
+    FastDiv tdiv[MAXD];
+    int64_t tstep[MAXO][MAXD];   // BYTES per tile step along d
     uint8_t tdim[MAXTD];
+    FastDiv outdiv;              // division by nouttiles (block id -> split, out tile)
     int64_t nouttiles;           // product of ntile over kept dims
     int64_t nrsteps;             // product of ntile over reduced dims
     int64_t steps_per_split;
@@ -134,10 +173,10 @@ struct ReduceParams {
     uint8_t dtype[MAXO];
     uint8_t conj[MAXO];
     OrderTab order;              // load order (input 1's fastest-stride order) over ALL tile dims
-    int64_t g_tstr[MAXO][MAXTD];
+    int64_t g_tstr[MAXO][MAXTD]; // BYTES
     int64_t g_joff[MAXO][MAXEPT];
     uint16_t jfield[MAXEPT][MAXTD];
-    int32_t s_tstr[MAXTD];       // shared-memory slot of (t, j) for the final in-CTA combine
+    int32_t s_tstr[MAXTD];       // shared-memory slot (elements) of (t, j) for the final in-CTA combine
     int32_t s_joff[MAXEPT];
     int32_t nout_tile;           // outputs per tile  = prod of kept tile extents
     int32_t nred_tile;           // partials per output = E / nout_tile

@@ -10,7 +10,7 @@
 
 namespace sb {
 
-template <class R> struct cx {
+template <class R> struct alignas(2 * sizeof(R)) cx {
     R re, im;
 };
 
@@ -197,51 +197,57 @@ template <class T> SB_HD T call2(int fn, T x, T y)
 template <class T> SB_HD T conj_of(T x) { return x; }
 template <class R> SB_HD cx<R> conj_of(cx<R> x) { return cx<R>{x.re, -x.im}; }
 
+// ---- CUDA vector type of the same size (for cache-hinted accesses) ---------------------------------------
+template <class T> struct vec_of;
+#if defined(__CUDACC__)
+template <> struct vec_of<float> { using type = float; };
+template <> struct vec_of<double> { using type = double; };
+template <> struct vec_of<cx<float>> { using type = float2; };
+template <> struct vec_of<cx<double>> { using type = double2; };
+SB_HD float to_vec(float x) { return x; }
+SB_HD double to_vec(double x) { return x; }
+SB_HD float2 to_vec(cx<float> x) { return make_float2(x.re, x.im); }
+SB_HD double2 to_vec(cx<double> x) { return make_double2(x.re, x.im); }
+#endif
+
 // ---- typed global loads/stores -------------------------------------------------------------------------
-// `UNIFORM`: storage type == compute type and no conj flag: a plain typed access.
-template <class CT, bool UNIFORM> SB_HD CT load_elem(const unsigned char *base, int64_t off, int dtype, int cj)
+// `p` is the BYTE address of the element.  `UNIFORM`: storage type == compute type and no conj flag: a plain
+// typed access (8/16-byte types become one LDG.64/LDG.128).
+template <class CT, bool UNIFORM> SB_HD CT load_elem(const unsigned char *p, int dtype, int cj)
 {
-    if (UNIFORM) return reinterpret_cast<const CT *>(base)[off];
+    if (UNIFORM) return *reinterpret_cast<const CT *>(p);
     CT v;
     switch (dtype) {
-    case F32: v = make<CT>((double)reinterpret_cast<const float *>(base)[off], 0.0); break;
-    case F64: v = make<CT>(reinterpret_cast<const double *>(base)[off], 0.0); break;
-    case C32: {
-        const float *p = reinterpret_cast<const float *>(base) + 2 * off;
-        v = make<CT>((double)p[0], (double)p[1]);
-        break;
-    }
-    default: {
-        const double *p = reinterpret_cast<const double *>(base) + 2 * off;
-        v = make<CT>(p[0], p[1]);
-        break;
-    }
+    case F32: v = make<CT>((double)*reinterpret_cast<const float *>(p), 0.0); break;
+    case F64: v = make<CT>(*reinterpret_cast<const double *>(p), 0.0); break;
+    case C32: v = make<CT>((double)reinterpret_cast<const float *>(p)[0], (double)reinterpret_cast<const float *>(p)[1]); break;
+    default: v = make<CT>(reinterpret_cast<const double *>(p)[0], reinterpret_cast<const double *>(p)[1]); break;
     }
     return cj ? conj_of(v) : v;
 }
 
-template <class CT, bool UNIFORM> SB_HD void store_elem(unsigned char *base, int64_t off, int dtype, int cj, CT v)
+template <class CT, bool UNIFORM> SB_HD void store_elem(unsigned char *p, int dtype, int cj, CT v)
 {
     if (UNIFORM) {
-        reinterpret_cast<CT *>(base)[off] = v;
+#if defined(__CUDA_ARCH__)
+        __stcs(reinterpret_cast<typename vec_of<CT>::type *>(p), to_vec(v)); // streaming store: the output is never re-read
+#else
+        *reinterpret_cast<CT *>(p) = v;
+#endif
         return;
     }
     if (cj) v = conj_of(v);
     switch (dtype) {
-    case F32: reinterpret_cast<float *>(base)[off] = (float)re_of(v); break;
-    case F64: reinterpret_cast<double *>(base)[off] = (double)re_of(v); break;
-    case C32: {
-        float *p = reinterpret_cast<float *>(base) + 2 * off;
-        p[0] = (float)re_of(v);
-        p[1] = (float)im_of(v);
+    case F32: *reinterpret_cast<float *>(p) = (float)re_of(v); break;
+    case F64: *reinterpret_cast<double *>(p) = (double)re_of(v); break;
+    case C32:
+        reinterpret_cast<float *>(p)[0] = (float)re_of(v);
+        reinterpret_cast<float *>(p)[1] = (float)im_of(v);
         break;
-    }
-    default: {
-        double *p = reinterpret_cast<double *>(base) + 2 * off;
-        p[0] = (double)re_of(v);
-        p[1] = (double)im_of(v);
+    default:
+        reinterpret_cast<double *>(p)[0] = (double)re_of(v);
+        reinterpret_cast<double *>(p)[1] = (double)im_of(v);
         break;
-    }
     }
 }
 

@@ -11,22 +11,28 @@ namespace sb {
 // Persistent CTAs: grid = min(ntiles, SMs x resident CTAs); each CTA walks tiles pos = blockIdx.x + i*grid,
 // so neighbouring CTAs work on neighbouring tiles at the same time (DRAM page / L2 locality, and aliased
 // operands such as A and A' meet in L2).
+// resident CTAs per SM the register allocator is asked to allow (value registers = NIN*EPT words of CT)
+template <class CT, int NIN, int EPT> struct MinBlocks {
+    static constexpr int words = NIN * EPT * (int)(sizeof(CT) / 4);
+    static constexpr int value = words <= 32 ? 4 : (words <= 64 ? 2 : 1);
+};
+
 template <class CT, int RC, int NIN, int EPT, bool UNIFORM>
-__global__ void __launch_bounds__(THREADS) map_tile_kernel(const __grid_constant__ MapParams P)
+__global__ void __launch_bounds__(THREADS, MinBlocks<CT, NIN, EPT>::value) map_tile_kernel(const __grid_constant__ MapParams P)
 {
     extern __shared__ __align__(16) unsigned char sb_smem_raw[];
-    CT *smem = reinterpret_cast<CT *>(sb_smem_raw);
     const int t = threadIdx.x;
     MapThread<NIN + 1> th;
     map_thread_init<NIN + 1>(P, t, th);
     const bool staged = P.nstaged > 0;
-    for (int64_t pos = blockIdx.x; pos < P.ntiles; pos += gridDim.x) {
-        MapTile tl;
-        map_tile_init(P, pos, tl);
+    const uint32_t ntiles = (uint32_t)P.ntiles;
+    for (uint32_t pos = blockIdx.x; pos < ntiles; pos += gridDim.x) {
+        MapTile<NIN + 1> tl;
+        map_tile_init<NIN + 1>(P, th, pos, tl);
         CT v[NIN][EPT];
-        map_phase1<CT, NIN, EPT, UNIFORM>(P, th, tl, t, v, smem);
+        map_phase1<CT, NIN, EPT, UNIFORM>(P, th, tl, t, v, sb_smem_raw);
         if (staged) __syncthreads();
-        map_phase2<CT, RC, NIN, EPT, UNIFORM>(P, th, tl, t, v, smem);
+        map_phase2<CT, RC, NIN, EPT, UNIFORM>(P, th, tl, t, v, sb_smem_raw);
         if (staged) __syncthreads();
     }
 }
@@ -46,12 +52,12 @@ template <class T> __device__ __forceinline__ T shfl_xor_any(T v, int mask)
 }
 
 template <class AT, int RC, int NIN, int EPT, bool UNIFORM>
-__global__ void __launch_bounds__(THREADS) reduce_tile_kernel(const __grid_constant__ ReduceParams P)
+__global__ void __launch_bounds__(THREADS, MinBlocks<AT, NIN, EPT>::value) reduce_tile_kernel(const __grid_constant__ ReduceParams P)
 {
     extern __shared__ __align__(16) unsigned char sb_smem_raw[];
     AT *smem = reinterpret_cast<AT *>(sb_smem_raw);
     const int t = threadIdx.x;
-    const int64_t bid = blockIdx.x;
+    const uint32_t bid = blockIdx.x;
     red_accumulate<AT, RC, NIN, EPT, UNIFORM>(P, bid, t, smem);
     __syncthreads();
     if (P.warp_per_output) {
@@ -69,8 +75,13 @@ __global__ void __launch_bounds__(THREADS) reduce_tile_kernel(const __grid_const
 
 template <class AT, bool UNIFORM> __global__ void __launch_bounds__(THREADS) reduce_finalize_kernel(const __grid_constant__ ReduceParams P)
 {
-    const int64_t idx = (int64_t)blockIdx.x * THREADS + threadIdx.x;
-    red_finalize<AT, UNIFORM>(P, idx);
+    const int64_t out_idx = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (out_idx >= P.nouttiles * (int64_t)P.nout_tile) return; // warp-uniform
+    AT p = red_finalize_lane<AT>(P, out_idx, lane);
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) p = red_apply<AT>(P.op, p, shfl_xor_any(p, m));
+    if (lane == 0) red_finalize_store<AT, UNIFORM>(P, out_idx, p);
 }
 
 // ---- registry ---------------------------------------------------------------------------------------------

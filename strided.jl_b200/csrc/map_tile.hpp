@@ -1,5 +1,5 @@
 // map_tile.hpp -- body of the N-D tiled strided map kernel (host/device neutral; the __global__ wrapper is
-// in kernels_map.cuh, a CPU thread-grid emulation for tests is in tests/emul/).
+// in kernels.cuh, a CPU thread-grid emulation for tests is in tests/emul/).
 //
 // One tile = a power-of-two box of THREADS*EPT elements.  Per tile, per thread:
 //   phase 1: issue ALL global loads of the tile (every input, each in its own fastest-stride order so a
@@ -11,20 +11,24 @@
 // This is the GPU replacement of the reference's blocked loop nest (src/mapreduce.jl:229-425, map mode
 // `A1[I1] = f(A2[I2], ...)`, :311): its cache blocks (`_computeblocks`, :463-500) become shared-memory
 // tiles, its loop-order heuristic (`_mapreduce_order!`, :119-139) becomes per-operand load orders.
+//
+// Cost discipline (profiles/r01_v0 -> r01_v1): everything per tile is O(ndim + nops) 32-bit work held in
+// registers (magic-number division, fully unrolled loops guarded by uniform predicates, no local arrays);
+// per element it is one 64-bit add per access (all functionals are pre-scaled to bytes).
 #pragma once
 #include "functors.hpp"
 
 namespace sb {
 
 template <int NOPS> struct MapThread {
-    int64_t g_toff[NOPS]; // global element offset contributed by t, operand k (its load order)
-    int32_t w_toff[NOPS]; // staging-buffer write slot contributed by t (own order)
-    int32_t r_toff[NOPS]; // staging-buffer read slot contributed by t (output order)
+    int64_t g_toff[NOPS]; // global BYTE offset contributed by t, operand k (its load order)
+    int32_t w_toff[NOPS]; // staging-buffer write byte offset contributed by t (own order)
+    int32_t r_toff[NOPS]; // staging-buffer read byte offset contributed by t (output order)
 };
 
-struct MapTile {
-    int64_t base[MAXO]; // element offset of the tile origin, per operand
-    int32_t rem[MAXTD]; // remaining extent per tile-dim slot (>= tile extent for interior tiles)
+template <int NOPS> struct MapTile {
+    const unsigned char *ptr[NOPS]; // operand base + byte offset of the tile origin
+    uint32_t id;
     bool full;
 };
 
@@ -32,121 +36,151 @@ template <int NOPS> SB_HD void map_thread_init(const MapParams &P, int t, MapThr
 {
 #pragma unroll
     for (int k = 0; k < NOPS; ++k) {
-        if (k >= P.nops) {
-            th.g_toff[k] = 0;
-            th.w_toff[k] = 0;
-            th.r_toff[k] = 0;
-            continue;
-        }
-        const OrderTab &o = P.order[k];
         int64_t g = 0;
-        int32_t w = 0;
-        for (int i = 0; i < o.n; ++i) {
-            const int f = field_of(o, i, t);
-            g += (int64_t)f * P.g_tstr[k][i];
-            w += f * P.w_tstr[k][i];
+        int32_t w = 0, r = 0;
+        if (k < P.nops) {
+            const OrderTab &o = P.order[k];
+            for (int i = 0; i < o.n; ++i) {
+                const int f = field_of(o, i, t);
+                g += (int64_t)f * P.g_tstr[k][i];
+                w += f * P.w_tstr[k][i];
+            }
+            const OrderTab &oo = P.order[0];
+            for (int i = 0; i < oo.n; ++i) r += field_of(oo, i, t) * P.r_tstr[k][i];
         }
         th.g_toff[k] = g;
         th.w_toff[k] = w;
-        int32_t r = 0;
-        const OrderTab &oo = P.order[0];
-        for (int i = 0; i < oo.n; ++i) r += field_of(oo, i, t) * P.r_tstr[k][i];
         th.r_toff[k] = r;
     }
 }
 
-SB_HD void map_tile_init(const MapParams &P, int64_t pos, MapTile &tl)
+template <int NOPS> SB_HD void map_tile_init(const MapParams &P, const MapThread<NOPS> &th, uint32_t pos, MapTile<NOPS> &tl)
 {
-    int64_t id = P.tile_order ? (int64_t)P.tile_order[pos] : pos;
-    for (int k = 0; k < MAXO; ++k) tl.base[k] = 0;
-    int32_t origin[MAXD];
-    for (int d = 0; d < P.ndim; ++d) {
-        const int64_t q = id / P.ntile[d];
-        const int32_t c = (int32_t)(id - q * P.ntile[d]);
-        id = q;
-        origin[d] = c * P.tile_b[d];
-        for (int k = 0; k < P.nops; ++k) tl.base[k] += (int64_t)origin[d] * P.strides[k][d];
-    }
+    uint32_t id = P.tile_order ? (uint32_t)P.tile_order[pos] : pos;
+    tl.id = id;
+    int64_t off[NOPS];
+#pragma unroll
+    for (int k = 0; k < NOPS; ++k) off[k] = th.g_toff[k];
     bool full = true;
-    for (int i = 0; i < P.ntd; ++i) {
-        const int d = P.tdim[i];
-        const int64_t r = P.dims[d] - origin[d];
-        tl.rem[i] = r > 0x7fffffff ? 0x7fffffff : (int32_t)r;
-        full = full && (r >= P.tile_b[d]);
+#pragma unroll
+    for (int d = 0; d < MAXD; ++d) {
+        if (d < P.ndim) {
+            uint32_t q, c;
+            fast_divmod(P.tdiv[d], id, q, c);
+            id = q;
+            full = full && ((int32_t)c < P.nfull[d]);
+#pragma unroll
+            for (int k = 0; k < NOPS; ++k)
+                if (k < P.nops) off[k] += (int64_t)c * P.tstep[k][d];
+        }
     }
+#pragma unroll
+    for (int k = 0; k < NOPS; ++k) tl.ptr[k] = P.base[k < P.nops ? k : 0] + off[k];
     tl.full = full;
 }
 
+// Remaining extent per tile-dim slot -- only needed on edge tiles (slow path, may use local memory).
+SB_HD void map_tile_rem(const MapParams &P, uint32_t id, int32_t (&rem)[MAXTD])
+{
+    int64_t origin[MAXD];
+    for (int d = 0; d < P.ndim; ++d) {
+        uint32_t q, c;
+        fast_divmod(P.tdiv[d], id, q, c);
+        id = q;
+        origin[d] = (int64_t)c * P.tile_b[d];
+    }
+    for (int i = 0; i < MAXTD; ++i) {
+        int64_t r = 1;
+        if (i < P.ntd) r = P.dims[P.tdim[i]] - origin[P.tdim[i]];
+        rem[i] = r > 0x7fffffff ? 0x7fffffff : (int32_t)r;
+    }
+}
+
 // is element (t, j) of operand k's traversal inside the array?  (only evaluated on edge tiles)
-SB_HD bool map_valid(const MapParams &P, const MapTile &tl, int k, int t, int j)
+SB_HD bool map_valid(const MapParams &P, const int32_t (&rem)[MAXTD], int k, int t, int j)
 {
     const OrderTab &o = P.order[k];
     bool ok = true;
     for (int i = 0; i < o.n; ++i) {
         const int c = field_of(o, i, t) + (int)P.jfield[k][j][i];
-        ok = ok && (c < tl.rem[o.td[i]]);
+        ok = ok && (c < rem[o.td[i]]);
     }
     return ok;
 }
 
 // Phase 1.  v[k-1][j] receives input k's element (t, j) in input k's LOAD order.
 template <class CT, int NIN, int EPT, bool UNIFORM>
-SB_HD void map_phase1(const MapParams &P, const MapThread<NIN + 1> &th, const MapTile &tl, int t, CT (&v)[NIN][EPT],
-                      CT *smem)
+SB_HD void map_phase1(const MapParams &P, const MapThread<NIN + 1> &th, const MapTile<NIN + 1> &tl, int t,
+                      CT (&v)[NIN][EPT], unsigned char *smem)
 {
+    if (tl.full) {
 #pragma unroll
-    for (int k = 1; k <= NIN; ++k) {
-        if (k >= P.nops) { // unused input slot of a wider instantiation
+        for (int k = 1; k <= NIN; ++k) {
+            if (k < P.nops) {
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) v[k - 1][j] = make<CT>(0.0, 0.0);
-            continue;
+                for (int j = 0; j < EPT; ++j) v[k - 1][j] = load_elem<CT, UNIFORM>(tl.ptr[k] + P.g_joff[k][j], P.dtype[k], P.conj[k]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < EPT; ++j) v[k - 1][j] = make<CT>(0.0, 0.0);
+            }
         }
-        const unsigned char *b = P.base[k];
-        const int64_t o0 = tl.base[k] + th.g_toff[k];
-        if (tl.full) {
+    } else {
+        int32_t rem[MAXTD];
+        map_tile_rem(P, tl.id, rem);
 #pragma unroll
-            for (int j = 0; j < EPT; ++j)
-                v[k - 1][j] = load_elem<CT, UNIFORM>(b, o0 + P.g_joff[k][j], P.dtype[k], P.conj[k]);
-        } else {
+        for (int k = 1; k <= NIN; ++k) {
 #pragma unroll
             for (int j = 0; j < EPT; ++j) {
                 CT x = make<CT>(0.0, 0.0);
-                if (map_valid(P, tl, k, t, j)) x = load_elem<CT, UNIFORM>(b, o0 + P.g_joff[k][j], P.dtype[k], P.conj[k]);
+                if (k < P.nops && map_valid(P, rem, k, t, j)) x = load_elem<CT, UNIFORM>(tl.ptr[k] + P.g_joff[k][j], P.dtype[k], P.conj[k]);
                 v[k - 1][j] = x;
             }
         }
     }
 #pragma unroll
     for (int k = 1; k <= NIN; ++k) {
-        if (k >= P.nops || !P.staged[k]) continue;
-        CT *s = smem + P.smem_off[k];
+        if (k < P.nops && P.staged[k]) {
+            unsigned char *s = smem + P.smem_off[k] + th.w_toff[k];
 #pragma unroll
-        for (int j = 0; j < EPT; ++j) s[th.w_toff[k] + P.w_joff[k][j]] = v[k - 1][j];
+            for (int j = 0; j < EPT; ++j) *reinterpret_cast<CT *>(s + P.w_joff[k][j]) = v[k - 1][j];
+        }
     }
 }
 
 // Phase 2 (after the barrier).
 template <class CT, int RC, int NIN, int EPT, bool UNIFORM>
-SB_HD void map_phase2(const MapParams &P, const MapThread<NIN + 1> &th, const MapTile &tl, int t, CT (&v)[NIN][EPT],
-                      const CT *smem)
+SB_HD void map_phase2(const MapParams &P, const MapThread<NIN + 1> &th, const MapTile<NIN + 1> &tl, int t,
+                      CT (&v)[NIN][EPT], const unsigned char *smem)
 {
 #pragma unroll
     for (int k = 1; k <= NIN; ++k) {
-        if (k >= P.nops || !P.staged[k]) continue;
-        const CT *s = smem + P.smem_off[k];
+        if (k < P.nops && P.staged[k]) {
+            const unsigned char *s = smem + P.smem_off[k] + th.r_toff[k];
 #pragma unroll
-        for (int j = 0; j < EPT; ++j) v[k - 1][j] = s[th.r_toff[k] + P.r_joff[k][j]];
+            for (int j = 0; j < EPT; ++j) v[k - 1][j] = *reinterpret_cast<const CT *>(s + P.r_joff[k][j]);
+        }
     }
     ElemFn<CT, RC> fn;
-    unsigned char *ob = P.base[0];
-    const int64_t o0 = tl.base[0] + th.g_toff[0];
+    unsigned char *ob = const_cast<unsigned char *>(tl.ptr[0]);
+    if (tl.full) {
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-        CT a[NIN];
+        for (int j = 0; j < EPT; ++j) {
+            CT a[NIN];
 #pragma unroll
-        for (int k = 0; k < NIN; ++k) a[k] = v[k][j];
-        const CT r = fn.template eval<NIN>(P.prog, a);
-        if (tl.full || map_valid(P, tl, 0, t, j)) store_elem<CT, UNIFORM>(ob, o0 + P.g_joff[0][j], P.dtype[0], P.conj[0], r);
+            for (int k = 0; k < NIN; ++k) a[k] = v[k][j];
+            store_elem<CT, UNIFORM>(ob + P.g_joff[0][j], P.dtype[0], P.conj[0], fn.template eval<NIN>(P.prog, a));
+        }
+    } else {
+        int32_t rem[MAXTD];
+        map_tile_rem(P, tl.id, rem);
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            CT a[NIN];
+#pragma unroll
+            for (int k = 0; k < NIN; ++k) a[k] = v[k][j];
+            const CT r = fn.template eval<NIN>(P.prog, a);
+            if (map_valid(P, rem, 0, t, j)) store_elem<CT, UNIFORM>(ob + P.g_joff[0][j], P.dtype[0], P.conj[0], r);
+        }
     }
 }
 

@@ -464,6 +464,133 @@ void fill_common_tables(const OrderTab &o, int ept, uint16_t (*jfield)[MAXTD])
         for (int i = 0; i < o.n; ++i) jfield[j][i] = (uint16_t)field_of(o, i, j * THREADS);
 }
 
+// ---- alias-aware tile order ------------------------------------------------------------------------------
+// Inputs that are dim-permuted views of the SAME parent (A and A' in `(A .+ A') ./ 2`; the four rotations of
+// config 4) read every parent byte once per view.  The reference's answer is cache blocking inside one task;
+// on the GPU the cache that can serve the second touch is L2 -- if both touches happen close in time.  This
+// builds a launch order in which the tiles whose DIRECT read regions are each other's permuted images run
+// next to each other (same wave): square "superblocks" closed under the permutation are visited orbit by
+// orbit.  Result: DRAM reads approach the compulsory bytes (SURVEY.md section 7 "Config 2 aliasing").
+bool build_tile_order(const Canon &c, const MapParams &P, std::vector<int32_t> &order)
+{
+    order.clear();
+    const int n = c.ndim;
+    if (P.ntiles < 4 || P.ntiles > (1 << 22)) return false;
+    // generators: dim permutations pi with  s_k'[d] == s_k[pi(d)]  for aliasing inputs k < k'
+    std::vector<std::vector<int>> gens;
+    for (int k2 = 2; k2 < c.nops; ++k2)
+        for (int k1 = 1; k1 < k2; ++k1) {
+            if (c.base[k1] != c.base[k2] || c.base[k1] == nullptr || c.dtype[k1] != c.dtype[k2]) continue;
+            std::vector<int> pi(n, -1);
+            std::vector<bool> used(n, false);
+            bool ok = true, ident = true;
+            for (int d = 0; d < n && ok; ++d) {
+                int hit = -1;
+                for (int e = 0; e < n; ++e)
+                    if (!used[e] && c.strides[k1][e] == c.strides[k2][d] && c.strides[k1][e] != 0 && c.dims[e] == c.dims[d]) {
+                        hit = e;
+                        break;
+                    }
+                if (hit < 0) ok = false;
+                else {
+                    pi[d] = hit;
+                    used[hit] = true;
+                    if (hit != d) ident = false;
+                }
+            }
+            if (ok && !ident) gens.push_back(pi);
+        }
+    if (gens.empty()) return false;
+    // superblock extents: constant along the orbits of every generator
+    int64_t S[MAXD];
+    for (int d = 0; d < n; ++d) S[d] = P.tile_b[d];
+    for (bool changed = true; changed;) {
+        changed = false;
+        for (const auto &pi : gens)
+            for (int d = 0; d < n; ++d) {
+                const int64_t m = std::max(S[d], S[pi[d]]);
+                if (S[d] != m || S[pi[d]] != m) {
+                    S[d] = S[pi[d]] = m;
+                    changed = true;
+                }
+            }
+    }
+    int64_t nsb[MAXD], r[MAXD], nsb_total = 1;
+    for (int d = 0; d < n; ++d) {
+        nsb[d] = (c.dims[d] + S[d] - 1) / S[d];
+        r[d] = S[d] / P.tile_b[d];
+        nsb_total *= nsb[d];
+    }
+    if (nsb_total > (1 << 22)) return false;
+    std::vector<uint8_t> seen((size_t)nsb_total, 0);
+    order.reserve((size_t)P.ntiles);
+    std::vector<int64_t> orbit, stack;
+    auto decode = [&](int64_t id, int64_t *cc) {
+        for (int d = 0; d < n; ++d) {
+            cc[d] = id % nsb[d];
+            id /= nsb[d];
+        }
+    };
+    auto encode = [&](const int64_t *cc) {
+        int64_t id = 0;
+        for (int d = n - 1; d >= 0; --d) id = id * nsb[d] + cc[d];
+        return id;
+    };
+    for (int64_t sb0 = 0; sb0 < nsb_total; ++sb0) {
+        if (seen[(size_t)sb0]) continue;
+        orbit.clear();
+        stack.assign(1, sb0);
+        seen[(size_t)sb0] = 1;
+        while (!stack.empty()) {
+            const int64_t cur = stack.back();
+            stack.pop_back();
+            orbit.push_back(cur);
+            int64_t cc[MAXD], nc[MAXD];
+            decode(cur, cc);
+            for (const auto &pi : gens)
+                for (int dir = 0; dir < 2; ++dir) {
+                    for (int d = 0; d < n; ++d) {
+                        if (dir == 0) nc[pi[d]] = cc[d]; // Phi
+                        else nc[d] = cc[pi[d]];          // Phi^-1
+                    }
+                    const int64_t nid = encode(nc);
+                    if (!seen[(size_t)nid]) {
+                        seen[(size_t)nid] = 1;
+                        stack.push_back(nid);
+                    }
+                }
+        }
+        for (const int64_t sb : orbit) { // all tiles of the superblock, natural order (dim 0 fastest)
+            int64_t cc[MAXD], lo[MAXD], hi[MAXD], t[MAXD];
+            decode(sb, cc);
+            bool empty = false;
+            for (int d = 0; d < n; ++d) {
+                lo[d] = cc[d] * r[d];
+                hi[d] = std::min<int64_t>(lo[d] + r[d], P.ntile[d]);
+                t[d] = lo[d];
+                if (lo[d] >= hi[d]) empty = true;
+            }
+            if (empty) continue;
+            for (;;) {
+                int64_t id = 0;
+                for (int d = n - 1; d >= 0; --d) id = id * P.ntile[d] + t[d];
+                order.push_back((int32_t)id);
+                int d = 0;
+                for (; d < n; ++d) {
+                    if (++t[d] < hi[d]) break;
+                    t[d] = lo[d];
+                }
+                if (d == n) break;
+            }
+        }
+    }
+    if ((int64_t)order.size() != P.ntiles) { // cannot happen; keep the natural order rather than a broken table
+        order.clear();
+        return false;
+    }
+    return true;
+}
+
 int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err)
 {
     MapParams &P = plan.map;
@@ -561,14 +688,20 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
         const int64_t nt = (c.dims[i] + P.tile_b[i] - 1) / P.tile_b[i];
         if (nt > 0x7fffffff) { err = "dim too large"; return SB_E_UNSUPPORTED; }
         P.ntile[i] = (int32_t)nt;
+        P.nfull[i] = (int32_t)(c.dims[i] / P.tile_b[i]);
+        P.tdiv[i] = make_fastdiv((uint32_t)nt);
         P.ntiles *= nt;
     }
+    if (P.ntiles > 0x7fffffff) { err = "too many tiles"; return SB_E_UNSUPPORTED; }
     for (int i = 0; i < ntd; ++i) P.tdim[i] = (uint8_t)tdim[i];
     for (int k = 0; k < nops; ++k) {
         P.base[k] = c.base[k];
         P.dtype[k] = (uint8_t)c.dtype[k];
         P.conj[k] = (uint8_t)c.conj[k];
-        for (int i = 0; i < n; ++i) P.strides[k][i] = c.strides[k][i];
+        for (int i = 0; i < n; ++i) {
+            P.strides[k][i] = c.strides[k][i];
+            P.tstep[k][i] = (int64_t)P.tile_b[i] * c.strides[k][i] * dtype_size(c.dtype[k]);
+        }
     }
     // orders
     int ident[MAXTD];
@@ -594,7 +727,7 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
     // functionals
     for (int k = 0; k < nops; ++k) {
         const OrderTab &o = P.order[k];
-        for (int i = 0; i < o.n; ++i) P.g_tstr[k][i] = c.strides[k][tdim[o.td[i]]];
+        for (int i = 0; i < o.n; ++i) P.g_tstr[k][i] = c.strides[k][tdim[o.td[i]]] * dtype_size(c.dtype[k]); // bytes
         for (int j = 0; j < ept; ++j) {
             int64_t g = 0;
             for (int i = 0; i < o.n; ++i) g += (int64_t)field_of(o, i, j * THREADS) * P.g_tstr[k][i];
@@ -604,11 +737,11 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
         if (k > 0 && P.staged[k]) {
             int32_t sigma[MAXTD];
             const int32_t len = choose_smem_strides(o, P.order[0], ntd, tbits, esz, sigma);
-            P.smem_off[k] = smem_elems;
+            P.smem_off[k] = smem_elems * esz; // bytes; staged values are stored as the compute type
             smem_elems += (len + 3) & ~3;
             const OrderTab &oo = P.order[0];
-            for (int i = 0; i < o.n; ++i) P.w_tstr[k][i] = sigma[o.td[i]];
-            for (int i = 0; i < oo.n; ++i) P.r_tstr[k][i] = sigma[oo.td[i]];
+            for (int i = 0; i < o.n; ++i) P.w_tstr[k][i] = sigma[o.td[i]] * esz;
+            for (int i = 0; i < oo.n; ++i) P.r_tstr[k][i] = sigma[oo.td[i]] * esz;
             for (int j = 0; j < ept; ++j) {
                 int32_t w = 0, r = 0;
                 for (int i = 0; i < o.n; ++i) w += field_of(o, i, j * THREADS) * P.w_tstr[k][i];
@@ -625,6 +758,7 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
     plan.smem_bytes = (int64_t)smem_elems * esz;
     if (plan.smem_bytes > 200 * 1024) { err = "staging buffers exceed shared memory"; return SB_E_UNSUPPORTED; }
     plan.grid = std::min<int64_t>(P.ntiles, (int64_t)dev.sm_count * dev.ctas_per_sm);
+    if (build_tile_order(c, P, plan.tile_order)) plan.note = "alias-aware tile order";
     plan.elements = 1;
     for (int i = 0; i < n; ++i) plan.elements *= c.dims[i];
     return SB_OK;
@@ -694,19 +828,26 @@ int plan_reduce(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &
         const int64_t nt = (c.dims[i] + P.tile_b[i] - 1) / P.tile_b[i];
         if (nt > 0x7fffffff) { err = "dim too large"; return SB_E_UNSUPPORTED; }
         P.ntile[i] = (int32_t)nt;
+        P.nfull[i] = (int32_t)(c.dims[i] / P.tile_b[i]);
+        P.tdiv[i] = make_fastdiv((uint32_t)nt);
         if (i < c.nkept) P.nouttiles *= nt;
         else P.nrsteps *= nt;
     }
+    if (P.nouttiles > 0x7fffffff || P.nrsteps > 0x7fffffff) { err = "too many tiles"; return SB_E_UNSUPPORTED; }
+    P.outdiv = make_fastdiv((uint32_t)P.nouttiles);
     for (int i = 0; i < ntd; ++i) P.tdim[i] = (uint8_t)tdim[i];
     for (int k = 0; k < nops; ++k) {
         P.base[k] = c.base[k];
         P.dtype[k] = (uint8_t)c.dtype[k];
         P.conj[k] = (uint8_t)c.conj[k];
-        for (int i = 0; i < n; ++i) P.strides[k][i] = c.strides[k][i];
+        for (int i = 0; i < n; ++i) {
+            P.strides[k][i] = c.strides[k][i];
+            P.tstep[k][i] = (int64_t)P.tile_b[i] * c.strides[k][i] * dtype_size(c.dtype[k]);
+        }
     }
     operand_order(c, 1, tdim, ntd, tbits, P.order);
     for (int k = 1; k < nops; ++k) {
-        for (int i = 0; i < P.order.n; ++i) P.g_tstr[k][i] = c.strides[k][tdim[P.order.td[i]]];
+        for (int i = 0; i < P.order.n; ++i) P.g_tstr[k][i] = c.strides[k][tdim[P.order.td[i]]] * dtype_size(c.dtype[k]); // bytes
         for (int j = 0; j < ept; ++j) {
             int64_t g = 0;
             for (int i = 0; i < P.order.n; ++i) g += (int64_t)field_of(P.order, i, j * THREADS) * P.g_tstr[k][i];
@@ -857,7 +998,7 @@ std::string describe_plan(const Plan &p)
         const MapParams &P = p.map;
         arr64("dims", P.dims, P.ndim);
         arr32("tile", P.tile_b, P.ndim);
-        os << ",\"ntiles\":" << P.ntiles << ",\"nstaged\":" << P.nstaged << ",\"staged\":[";
+        os << ",\"ntiles\":" << P.ntiles << ",\"tile_order\":" << (p.tile_order.empty() ? 0 : 1) << ",\"nstaged\":" << P.nstaged << ",\"staged\":[";
         for (int k = 0; k < P.nops; ++k) os << (k ? "," : "") << (int)P.staged[k];
         os << "],\"strides\":[";
         for (int k = 0; k < P.nops; ++k) {

@@ -8,6 +8,7 @@
 #include "common.hpp"
 #include "../../include/strided_b200.h"
 #include <string>
+#include <vector>
 
 namespace sb {
 
@@ -39,6 +40,7 @@ struct Plan {
     std::string family;             // "map_tile" | "reduce_tile" | "noop"
     int base_src[MAXO] = {0, 1, 2, 3, 4, 5, 6, 7}; // canonical operand k reads sb_desc::base[base_src[k]]
     // optional alias-aware tile order (host copy; uploaded by the ctx)
+    std::vector<int32_t> tile_order; // launch position -> tile id (empty: natural order)
     std::string note;
 };
 

@@ -16,119 +16,141 @@
 
 namespace sb {
 
-struct RedCta {
-    int64_t out_tile, split;
-    int64_t kbase[MAXO]; // element offset of the output tile origin (kept dims), per operand
-    int32_t rem[MAXTD];  // remaining extent per tile-dim slot; kept slots fixed, reduced slots per step
+template <int NIN> struct RedCta {
+    const unsigned char *ptr[NIN]; // input k+1: base + kept-tile origin + thread offset (bytes)
+    uint32_t out_tile, split;
     bool kept_full;
 };
 
-SB_HD void red_cta_init(const ReduceParams &P, int64_t bid, RedCta &c)
+template <int NIN> SB_HD void red_cta_init(const ReduceParams &P, uint32_t bid, int t, RedCta<NIN> &c)
 {
-    c.out_tile = bid % P.nouttiles;
-    c.split = bid / P.nouttiles;
-    for (int k = 0; k < MAXO; ++k) c.kbase[k] = 0;
-    int64_t id = c.out_tile;
-    bool full = true;
-    for (int i = 0; i < MAXTD; ++i) c.rem[i] = 1;
-    for (int d = 0; d < P.nkept; ++d) {
-        const int64_t q = id / P.ntile[d];
-        const int64_t cd = id - q * P.ntile[d];
-        id = q;
-        const int64_t origin = cd * P.tile_b[d];
-        for (int k = 0; k < P.nops; ++k) c.kbase[k] += origin * P.strides[k][d];
-        const int64_t r = P.dims[d] - origin;
-        full = full && (r >= P.tile_b[d]);
-        for (int i = 0; i < P.ntd; ++i)
-            if (P.tdim[i] == d) c.rem[i] = r > 0x7fffffff ? 0x7fffffff : (int32_t)r;
+    uint32_t q, r;
+    fast_divmod(P.outdiv, bid, q, r);
+    c.out_tile = r;
+    c.split = q;
+    int64_t off[NIN];
+#pragma unroll
+    for (int k = 0; k < NIN; ++k) {
+        int64_t g = 0;
+        if (k + 1 < P.nops)
+            for (int i = 0; i < P.order.n; ++i) g += (int64_t)field_of(P.order, i, t) * P.g_tstr[k + 1][i];
+        off[k] = g;
     }
+    uint32_t id = c.out_tile;
+    bool full = true;
+#pragma unroll
+    for (int d = 0; d < MAXD; ++d) {
+        if (d < P.nkept) {
+            uint32_t qq, cd;
+            fast_divmod(P.tdiv[d], id, qq, cd);
+            id = qq;
+            full = full && ((int32_t)cd < P.nfull[d]);
+#pragma unroll
+            for (int k = 0; k < NIN; ++k)
+                if (k + 1 < P.nops) off[k] += (int64_t)cd * P.tstep[k + 1][d];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NIN; ++k) c.ptr[k] = P.base[k + 1 < P.nops ? k + 1 : 0] + off[k];
     c.kept_full = full;
 }
 
-// decode reduction step -> per-operand offset of the step origin; updates rem[] of reduced slots
-SB_HD bool red_step_init(const ReduceParams &P, RedCta &c, int64_t step, int64_t (&sbase)[MAXO])
+// decode reduction step -> byte offset of the step origin per input; returns "tile is interior"
+template <int NIN> SB_HD bool red_step_init(const ReduceParams &P, const RedCta<NIN> &c, uint32_t step, int64_t (&soff)[NIN])
 {
-    for (int k = 0; k < MAXO; ++k) sbase[k] = c.kbase[k];
+#pragma unroll
+    for (int k = 0; k < NIN; ++k) soff[k] = 0;
     bool full = c.kept_full;
-    int64_t id = step;
-    for (int d = P.nkept; d < P.ndim; ++d) {
-        const int64_t q = id / P.ntile[d];
-        const int64_t cd = id - q * P.ntile[d];
-        id = q;
-        const int64_t origin = cd * P.tile_b[d];
-        for (int k = 1; k < P.nops; ++k) sbase[k] += origin * P.strides[k][d];
-        const int64_t r = P.dims[d] - origin;
-        full = full && (r >= P.tile_b[d]);
-        for (int i = 0; i < P.ntd; ++i)
-            if (P.tdim[i] == d) c.rem[i] = r > 0x7fffffff ? 0x7fffffff : (int32_t)r;
+    uint32_t id = step;
+#pragma unroll
+    for (int d = 0; d < MAXD; ++d) {
+        if (d >= P.nkept && d < P.ndim) {
+            uint32_t q, cd;
+            fast_divmod(P.tdiv[d], id, q, cd);
+            id = q;
+            full = full && ((int32_t)cd < P.nfull[d]);
+#pragma unroll
+            for (int k = 0; k < NIN; ++k)
+                if (k + 1 < P.nops) soff[k] += (int64_t)cd * P.tstep[k + 1][d];
+        }
     }
     return full;
 }
 
-SB_HD bool red_valid(const ReduceParams &P, const RedCta &c, int t, int j)
+// remaining extents per tile-dim slot for (out_tile, step): edge tiles only (slow path)
+SB_HD void red_rem(const ReduceParams &P, uint32_t out_tile, uint32_t step, int32_t (&rem)[MAXTD])
+{
+    int64_t origin[MAXD];
+    uint32_t id = out_tile;
+    for (int d = 0; d < P.ndim; ++d) {
+        if (d == P.nkept) id = step;
+        uint32_t q, cd;
+        fast_divmod(P.tdiv[d], id, q, cd);
+        id = q;
+        origin[d] = (int64_t)cd * P.tile_b[d];
+    }
+    for (int i = 0; i < MAXTD; ++i) {
+        int64_t r = 1;
+        if (i < P.ntd) r = P.dims[P.tdim[i]] - origin[P.tdim[i]];
+        rem[i] = r > 0x7fffffff ? 0x7fffffff : (int32_t)r;
+    }
+}
+
+SB_HD bool red_valid(const ReduceParams &P, const int32_t (&rem)[MAXTD], int t, int j)
 {
     bool ok = true;
     for (int i = 0; i < P.order.n; ++i) {
         const int f = field_of(P.order, i, t) + (int)P.jfield[j][i];
-        ok = ok && (f < c.rem[P.order.td[i]]);
+        ok = ok && (f < rem[P.order.td[i]]);
     }
     return ok;
 }
 
 // Accumulation phase of one CTA for thread t.  Leaves the EPT accumulators in shared memory.
 template <class AT, int RC, int NIN, int EPT, bool UNIFORM>
-SB_HD void red_accumulate(const ReduceParams &P, int64_t bid, int t, AT *smem)
+SB_HD void red_accumulate(const ReduceParams &P, uint32_t bid, int t, AT *smem)
 {
-    RedCta c;
-    red_cta_init(P, bid, c);
-    int64_t g_toff[NIN];
-#pragma unroll
-    for (int k = 1; k <= NIN; ++k) {
-        int64_t g = 0;
-        if (k < P.nops)
-            for (int i = 0; i < P.order.n; ++i) g += (int64_t)field_of(P.order, i, t) * P.g_tstr[k][i];
-        g_toff[k - 1] = g;
-    }
+    RedCta<NIN> c;
+    red_cta_init<NIN>(P, bid, t, c);
     AT acc[EPT];
 #pragma unroll
     for (int j = 0; j < EPT; ++j) acc[j] = red_neutral<AT>(P.op);
     ElemFn<AT, RC> fn;
-    const int64_t s0 = c.split * P.steps_per_split;
+    const int64_t s0 = (int64_t)c.split * P.steps_per_split;
     int64_t s1 = s0 + P.steps_per_split;
     if (s1 > P.nrsteps) s1 = P.nrsteps;
     for (int64_t step = s0; step < s1; ++step) {
-        int64_t sbase[MAXO];
-        const bool full = red_step_init(P, c, step, sbase);
+        int64_t soff[NIN];
+        const bool full = red_step_init<NIN>(P, c, (uint32_t)step, soff);
         AT v[NIN][EPT];
+        if (full) {
 #pragma unroll
-        for (int k = 1; k <= NIN; ++k) {
-            if (k >= P.nops) {
-#pragma unroll
-                for (int j = 0; j < EPT; ++j) v[k - 1][j] = make<AT>(0.0, 0.0);
-                continue;
-            }
-            const unsigned char *b = P.base[k];
-            const int64_t o0 = sbase[k] + g_toff[k - 1];
-            if (full) {
+            for (int k = 0; k < NIN; ++k) {
+                const unsigned char *b = c.ptr[k] + soff[k];
 #pragma unroll
                 for (int j = 0; j < EPT; ++j)
-                    v[k - 1][j] = load_elem<AT, UNIFORM>(b, o0 + P.g_joff[k][j], P.dtype[k], P.conj[k]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < EPT; ++j) {
-                    AT x = make<AT>(0.0, 0.0);
-                    if (red_valid(P, c, t, j)) x = load_elem<AT, UNIFORM>(b, o0 + P.g_joff[k][j], P.dtype[k], P.conj[k]);
-                    v[k - 1][j] = x;
-                }
+                    v[k][j] = (k + 1 < P.nops) ? load_elem<AT, UNIFORM>(b + P.g_joff[k + 1][j], P.dtype[k + 1], P.conj[k + 1]) : make<AT>(0.0, 0.0);
             }
-        }
 #pragma unroll
-        for (int j = 0; j < EPT; ++j) {
-            AT a[NIN];
+            for (int j = 0; j < EPT; ++j) {
+                AT a[NIN];
 #pragma unroll
-            for (int k = 0; k < NIN; ++k) a[k] = v[k][j];
-            const AT r = fn.template eval<NIN>(P.prog, a);
-            if (full || red_valid(P, c, t, j)) acc[j] = red_apply<AT>(P.op, acc[j], r);
+                for (int k = 0; k < NIN; ++k) a[k] = v[k][j];
+                acc[j] = red_apply<AT>(P.op, acc[j], fn.template eval<NIN>(P.prog, a));
+            }
+        } else {
+            int32_t rem[MAXTD];
+            red_rem(P, c.out_tile, (uint32_t)step, rem);
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) {
+                if (!red_valid(P, rem, t, j)) continue;
+                AT a[NIN];
+#pragma unroll
+                for (int k = 0; k < NIN; ++k)
+                    a[k] = (k + 1 < P.nops) ? load_elem<AT, UNIFORM>(c.ptr[k] + soff[k] + P.g_joff[k + 1][j], P.dtype[k + 1], P.conj[k + 1])
+                                            : make<AT>(0.0, 0.0);
+                acc[j] = red_apply<AT>(P.op, acc[j], fn.template eval<NIN>(P.prog, a));
+            }
         }
     }
     int32_t s_toff = 0;
@@ -153,58 +175,64 @@ template <class AT> SB_HD AT red_thread_partial(const ReduceParams &P, const AT 
     return p;
 }
 
-// output number o of a tile -> (valid, element offset in the output)
-SB_HD bool red_out_locate(const ReduceParams &P, int64_t out_tile, int o, int64_t &off)
+// output number o of a tile -> (valid, BYTE offset in the output)
+SB_HD bool red_out_locate(const ReduceParams &P, uint32_t out_tile, int o, int64_t &off)
 {
-    // tile origin over kept dims
-    int64_t id = out_tile;
+    uint32_t id = out_tile;
     int64_t origin[MAXD];
     off = 0;
     for (int d = 0; d < P.nkept; ++d) {
-        const int64_t q = id / P.ntile[d];
-        origin[d] = (id - q * P.ntile[d]) * P.tile_b[d];
+        uint32_t q, cd;
+        fast_divmod(P.tdiv[d], id, q, cd);
         id = q;
-        off += origin[d] * P.strides[0][d];
+        origin[d] = (int64_t)cd * P.tile_b[d];
+        off += (int64_t)cd * P.tstep[0][d];
     }
     bool ok = true;
     for (int i = 0; i < P.kept_order.n; ++i) {
         const int d = P.tdim[P.kept_order.td[i]];
         const int64_t cd = field_of(P.kept_order, i, o);
         ok = ok && (origin[d] + cd < P.dims[d]);
-        off += cd * P.strides[0][d];
+        off += cd * P.strides[0][d] * dtype_size(P.dtype[0]);
     }
     return ok;
 }
 
 // lane-0 / owning-thread epilogue for output o with in-CTA partial p
-template <class AT, bool UNIFORM> SB_HD void red_finish(const ReduceParams &P, int64_t bid, int o, AT p)
+template <class AT, bool UNIFORM> SB_HD void red_finish(const ReduceParams &P, uint32_t bid, int o, AT p)
 {
-    const int64_t out_tile = bid % P.nouttiles, split = bid / P.nouttiles;
+    uint32_t split, out_tile;
+    fast_divmod(P.outdiv, bid, split, out_tile);
     if (P.nsplit > 1) {
-        reinterpret_cast<AT *>(P.scratch)[(split * P.nouttiles + out_tile) * P.nout_tile + o] = p;
+        reinterpret_cast<AT *>(P.scratch)[((int64_t)split * P.nouttiles + out_tile) * P.nout_tile + o] = p;
         return;
     }
     int64_t off;
     if (!red_out_locate(P, out_tile, o, off)) return;
-    AT x = load_elem<AT, UNIFORM>(P.base[0], off, P.dtype[0], P.conj[0]);
+    AT x = load_elem<AT, UNIFORM>(P.base[0] + off, P.dtype[0], P.conj[0]);
     x = init_apply<AT>(P.initop, P.init_re, P.init_im, x);
-    store_elem<AT, UNIFORM>(P.base[0], off, P.dtype[0], P.conj[0], red_apply<AT>(P.op, x, p));
+    store_elem<AT, UNIFORM>(P.base[0] + off, P.dtype[0], P.conj[0], red_apply<AT>(P.op, x, p));
 }
 
-// finalize kernel body: one thread per (out_tile, o); folds the nsplit partials in split order
-template <class AT, bool UNIFORM> SB_HD void red_finalize(const ReduceParams &P, int64_t idx)
+// finalize kernel: one WARP per output (out_tile, o).  Lane l folds partials of splits l, l+32, ... in split
+// order; the 32 lane results are then combined by a shuffle butterfly (fixed order -> deterministic).
+template <class AT> SB_HD AT red_finalize_lane(const ReduceParams &P, int64_t out_idx, int lane)
 {
-    const int64_t out_tile = idx / P.nout_tile;
-    const int o = (int)(idx - out_tile * P.nout_tile);
-    if (out_tile >= P.nouttiles) return;
-    int64_t off;
-    if (!red_out_locate(P, out_tile, o, off)) return;
     const AT *sc = reinterpret_cast<const AT *>(P.scratch);
-    AT p = sc[(0 * P.nouttiles + out_tile) * P.nout_tile + o];
-    for (int s = 1; s < P.nsplit; ++s) p = red_apply<AT>(P.op, p, sc[((int64_t)s * P.nouttiles + out_tile) * P.nout_tile + o]);
-    AT x = load_elem<AT, UNIFORM>(P.base[0], off, P.dtype[0], P.conj[0]);
+    const int64_t stride = P.nouttiles * (int64_t)P.nout_tile;
+    AT p = red_neutral<AT>(P.op);
+    for (int s = lane; s < P.nsplit; s += 32) p = red_apply<AT>(P.op, p, sc[(int64_t)s * stride + out_idx]);
+    return p;
+}
+template <class AT, bool UNIFORM> SB_HD void red_finalize_store(const ReduceParams &P, int64_t out_idx, AT p)
+{
+    const int64_t out_tile = out_idx / P.nout_tile;
+    const int o = (int)(out_idx - out_tile * P.nout_tile);
+    int64_t off;
+    if (!red_out_locate(P, (uint32_t)out_tile, o, off)) return;
+    AT x = load_elem<AT, UNIFORM>(P.base[0] + off, P.dtype[0], P.conj[0]);
     x = init_apply<AT>(P.initop, P.init_re, P.init_im, x);
-    store_elem<AT, UNIFORM>(P.base[0], off, P.dtype[0], P.conj[0], red_apply<AT>(P.op, x, p));
+    store_elem<AT, UNIFORM>(P.base[0] + off, P.dtype[0], P.conj[0], red_apply<AT>(P.op, x, p));
 }
 
 } // namespace sb

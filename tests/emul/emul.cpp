@@ -20,18 +20,20 @@ static std::string g_err;
 template <class CT, int RC, int NIN, int EPT, bool U> static void run_map(const Plan &plan, int grid)
 {
     const MapParams &P = plan.map;
-    std::vector<CT> smem((size_t)plan.smem_bytes / sizeof(CT) + 16);
+    std::vector<unsigned char> smem((size_t)plan.smem_bytes + 64);
     std::vector<MapThread<NIN + 1>> th(THREADS);
     for (int t = 0; t < THREADS; ++t) map_thread_init<NIN + 1>(P, t, th[t]);
     using Regs = CT[NIN][EPT];
     std::vector<char> regbuf(sizeof(Regs) * THREADS);
     Regs *v = reinterpret_cast<Regs *>(regbuf.data());
     for (int b = 0; b < grid; ++b)
-        for (int64_t pos = b; pos < P.ntiles; pos += grid) {
-            MapTile tl;
-            map_tile_init(P, pos, tl);
-            for (int t = 0; t < THREADS; ++t) map_phase1<CT, NIN, EPT, U>(P, th[t], tl, t, v[t], smem.data());
-            for (int t = 0; t < THREADS; ++t) map_phase2<CT, RC, NIN, EPT, U>(P, th[t], tl, t, v[t], smem.data());
+        for (uint32_t pos = (uint32_t)b; pos < (uint32_t)P.ntiles; pos += (uint32_t)grid) {
+            std::vector<MapTile<NIN + 1>> tl(THREADS); // the tile descriptor is per thread (it folds the thread offset in)
+            for (int t = 0; t < THREADS; ++t) {
+                map_tile_init<NIN + 1>(P, th[t], pos, tl[t]);
+                map_phase1<CT, NIN, EPT, U>(P, th[t], tl[t], t, v[t], smem.data());
+            }
+            for (int t = 0; t < THREADS; ++t) map_phase2<CT, RC, NIN, EPT, U>(P, th[t], tl[t], t, v[t], smem.data());
         }
 }
 
@@ -39,7 +41,7 @@ template <class AT, int RC, int NIN, int EPT, bool U> static void run_reduce(con
 {
     const ReduceParams &P = plan.red;
     std::vector<AT> smem((size_t)THREADS * EPT);
-    for (int64_t bid = 0; bid < plan.grid; ++bid) {
+    for (uint32_t bid = 0; bid < (uint32_t)plan.grid; ++bid) {
         for (int t = 0; t < THREADS; ++t) red_accumulate<AT, RC, NIN, EPT, U>(P, bid, t, smem.data());
         if (P.warp_per_output) {
             for (int warp = 0; warp < THREADS / 32; ++warp)
@@ -59,8 +61,16 @@ template <class AT, int RC, int NIN, int EPT, bool U> static void run_reduce(con
         }
     }
     if (plan.finalize_threads > 0) {
-        const int64_t g = (plan.finalize_threads + THREADS - 1) / THREADS;
-        for (int64_t idx = 0; idx < g * THREADS; ++idx) red_finalize<AT, U>(P, idx);
+        for (int64_t out_idx = 0; out_idx < plan.finalize_threads; ++out_idx) {
+            AT p[32];
+            for (int lane = 0; lane < 32; ++lane) p[lane] = red_finalize_lane<AT>(P, out_idx, lane);
+            for (int m = 16; m >= 1; m >>= 1) {
+                AT q[32];
+                for (int lane = 0; lane < 32; ++lane) q[lane] = red_apply<AT>(P.op, p[lane], p[lane ^ m]);
+                std::memcpy(p, q, sizeof p);
+            }
+            red_finalize_store<AT, U>(P, out_idx, p[0]);
+        }
     }
 }
 
@@ -129,6 +139,7 @@ extern "C" int emul_mapreduce(const sb_desc *desc, int grid_limit)
     int rc = build_plan(*desc, dev, plan, g_err);
     if (rc != SB_OK) return rc;
     if (plan.kind == PLAN_NOOP) return SB_OK;
+    if (!plan.tile_order.empty()) plan.map.tile_order = plan.tile_order.data();
     bool ok = false;
     if (plan.kind == PLAN_MAP) {
         int grid = (int)plan.grid;
