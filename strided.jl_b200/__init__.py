@@ -17,4 +17,7 @@ from .engine import get_engine, make_desc, run_mapreduce, similar_parent
 from .mapreduce import (map_, map, copy_, conj_, adjoint_, transpose_, permutedims_, mapreduce, mapreducedim_,
                         _mapreducedim_, sum, prod, maximum, minimum, rmul_, lmul_, mul_, axpy_, axpby_)
 
+from . import sharded
+from .sharded import sharded_mapreduce, sharded_map_, shard_view, shard_range
+
 __all__ = [n for n in dir() if not n.startswith("__")]

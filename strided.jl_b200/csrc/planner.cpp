@@ -426,15 +426,33 @@ int32_t choose_smem_strides(const OrderTab &own, const OrderTab &out, int ntd, c
     return best_len;
 }
 
-int default_ept(int ct, int nin, int64_t needed)
+// which (compute type, EPT) tuples exist for the pre-instantiated recipes (tools/gen_kernel_units.py)
+bool ept_instantiated(int ct, int recipe, int nin_t, int ept, bool uniform)
 {
-    // value registers per thread ~ nin * EPT * words; instantiated: f32 {8,16}, f64 {8}, c32 {8}, c64 {4}
+    const int base = (ct == C64) ? 4 : 8;
+    if (recipe == RC_INTERP || !uniform) return ept == base;
+    const int words = nin_t * ept * (dtype_size(ct) / 4);
     switch (ct) {
-    case F32: return (needed > THREADS * 8 && nin <= 4) ? 16 : 8;
-    case F64: return 8;
-    case C32: return 8;
-    default: return 4;
+    case F32: return (ept == 4 || ept == 8 || ept == 16) && !(ept == 16 && words > 64);
+    case F64: return (ept == 4 || ept == 8 || ept == 16) && !(ept == 16 && words > 64);
+    case C32: return ept == 4 || ept == 8;
+    default: return ept == 4;
     }
+}
+
+int default_ept(int ct, int recipe, int nin_t, bool uniform, int64_t needed, int64_t elements, const DeviceInfo &dev)
+{
+    int ept = (ct == C64) ? 4 : 8;
+    if (ct == F32 && needed > THREADS * 8) ept = 16; // four hot dims x 32-byte runs (config 4)
+    // small problems: more, smaller tiles so that every SM gets an even share (one-wave kernels)
+    while (ept > 4 && elements / ((int64_t)THREADS * ept) < 4 * (int64_t)dev.sm_count && needed <= THREADS * (ept / 2)) ept /= 2;
+    if (const char *e = std::getenv("SB_FORCE_EPT")) { // tuning knob (tools/, never set in production)
+        const int v = std::atoi(e);
+        if (v == 4 || v == 8 || v == 16) ept = v;
+    }
+    while (ept > 4 && !ept_instantiated(ct, recipe, nin_t, ept, uniform)) ept /= 2;
+    if (!ept_instantiated(ct, recipe, nin_t, ept, uniform)) ept = (ct == C64) ? 4 : 8;
+    return ept;
 }
 
 int template_nin(int recipe, int nin)
@@ -629,7 +647,9 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
     int64_t needed = 1;
     for (int i = 0; i < n; ++i)
         if (hot[i]) needed <<= std::min(cap[i], minrun_bits);
-    const int ept = default_ept(c.ct, nin, needed);
+    int64_t elements = 1;
+    for (int i = 0; i < n; ++i) elements *= c.dims[i];
+    const int ept = default_ept(c.ct, P.prog.recipe, template_nin(P.prog.recipe, nin), uniform, needed, elements, dev);
     const int ebits = LOG_THREADS + ilog2_ceil(ept);
     int used = 0;
     // phase 1: a sector-sized run along every hot dim

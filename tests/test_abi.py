@@ -49,12 +49,14 @@ def test_plans_for_baseline_configs():
     p = case_c2(4000).plan()
     assert p["family"] == "map_tile" and p["recipe"] == "add2_mul" and p["ct"] == "f64"
     assert p["tile"] == [64, 32] and p["staged"] == [0, 0, 1] and p["ntiles"] == 63 * 125
+    assert p["tile_order"] == 1  # A and A' alias: tiles (I,J),(J,I) are launched side by side
     p = case_c1(1000).plan()
-    assert p["recipe"] == "scale" and p["staged"] == [0, 1]
-    p = case_c3(32).plan()
-    assert p["recipe"] == "copy" and p["dims"] == [32, 32, 32, 32] and p["tile"] == [32, 2, 1, 32]
+    assert p["recipe"] == "scale" and p["staged"] == [0, 1] and p["tile_order"] == 0
+    p = case_c3(32).plan()  # one-wave problem: smaller tiles so that every SM gets work
+    assert p["recipe"] == "copy" and p["dims"] == [32, 32, 32, 32] and p["tile"] == [32, 1, 1, 32] and p["ept"] == 4
     p = case_c4(64).plan()
     assert p["recipe"] == "sum4" and p["ept"] == 16 and p["tile"] == [8, 8, 8, 8] and p["staged"] == [0, 0, 1, 1, 1]
+    assert p["tile_order"] == 1
     p = case_c5(8, 4096).plan()
     assert p["family"] == "reduce_tile" and p["recipe"] == "abs2" and p["dims"] == [8, 16777216]
     assert p["tile"] == [8, 256] and p["nout_tile"] == 8 and p["nred_tile"] == 256 and p["nsplit"] > 100
