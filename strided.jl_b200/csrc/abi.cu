@@ -2,7 +2,7 @@
 //
 // There is NO CPU execution path here: without a CUDA device every compute entry point returns
 // SB_E_NODEVICE.  (sb_plan_describe is pure host planning and works anywhere.)
-#include "kernels.cuh"
+#include "tma_kernel.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -49,6 +49,53 @@ const ReduceEntry *find_reduce_kernel(const KernelKey &k)
 } // namespace sb
 
 static thread_local std::string g_tls_err;
+
+// cuTensorMapEncodeTiled is fetched through the runtime (no link-time dependency on libcuda, so the library
+// also loads on machines without a driver -- where it can only plan, not compute).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+static bool encode_tma_maps(const Plan &plan, CUtensorMap *maps)
+{
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return false;
+    const int nin = plan.tma.nin;
+    for (int k = 0; k < nin; ++k) {
+        const Plan::TmaGlobal &g = plan.tma_global[k];
+        void *base = plan.map.base[k + 1];
+        if (((uintptr_t)base & 15u) != 0) return false;
+        cuuint64_t gdim[TMA_MAXRANK], gstr[TMA_MAXRANK];
+        cuuint32_t box[TMA_MAXRANK], estr[TMA_MAXRANK];
+        for (int i = 0; i < g.rank; ++i) {
+            gdim[i] = g.gdim[i];
+            box[i] = g.box[i];
+            estr[i] = 1;
+            if (i > 0) gstr[i - 1] = g.gstride_bytes[i];
+        }
+        const CUtensorMapDataType dt = g.elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                       : (plan.key.ct == F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_UINT64);
+        const CUresult r = enc(&maps[k], dt, (cuuint32_t)g.rank, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               g.swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return false;
+    }
+    for (int k = nin; k < TMA_MAXIN; ++k) maps[k] = maps[0];
+    return true;
+}
 
 struct CachedPlan {
     Plan plan;
@@ -313,6 +360,21 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
     }
     if (plan.kind == PLAN_NOOP) return SB_OK;
     cudaSetDevice(ctx->device);
+    if (plan.kind == PLAN_MAP && plan.tma_ok) { // TMA-pipelined variant when the inputs qualify at bind time
+        const TmaEntry *tk = find_tma_kernel(plan.key);
+        alignas(64) CUtensorMap maps[TMA_MAXIN];
+        if (tk && encode_tma_maps(plan, maps)) {
+            int nb = 1;
+            rc = occupancy_of(ctx, tk->func, tk->occupancy, (size_t)plan.tma_smem_bytes, nb);
+            if (rc != SB_OK) return rc;
+            int64_t grid = std::min<int64_t>(plan.map.ntiles, (int64_t)ctx->dev.sm_count * nb);
+            if (grid < 1) grid = 1;
+            cudaError_t e = tk->launch(plan.map, plan.tma, maps, (int)grid, (size_t)plan.tma_smem_bytes, ctx->stream);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "map_tma launch");
+            ctx->stats.launches++;
+            return SB_OK;
+        }
+    }
     if (plan.kind == PLAN_MAP) {
         const MapEntry *k = find_map_kernel(plan.key);
         if (!k) return set_err(ctx, SB_E_UNSUPPORTED, "no map kernel instantiated for this plan");

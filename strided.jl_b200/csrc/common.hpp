@@ -152,6 +152,41 @@ struct MapParams {
     Program prog;
 };
 
+// ---- TMA-staged map plan ------------------------------------------------------------------------------------
+// Same tile decomposition as MapParams, but every INPUT tile is fetched by the Tensor Memory Accelerator
+// (cp.async.bulk.tensor) into a multi-stage shared-memory ring, several tiles ahead of the consumers.
+// Operands whose fastest dim is not the output's ("staged": the permutedims / transpose case) are written with
+// the 128-byte swizzle so that the transposed read is (almost) bank-conflict free; the consumer address of
+// element (t, j) is  S_t XOR s_joff[j]  because the dense box layout is a power-of-two bit-field layout and
+// the swizzle  D ^ (((D >> 7) & 7) << 4)  is linear over GF(2).
+constexpr int TMA_MAXIN = 4;
+constexpr int TMA_MAXRANK = 5;
+struct TmaOperand {
+    int32_t rank;                // tensor-map rank = canonical ndim, dims in the operand's own stride order
+    int32_t nbox;                // boxes per tile (inner dim split into 128-byte rows when swizzled)
+    int32_t box_bytes;
+    int32_t smem_off;            // byte offset inside a stage (multiple of 1024)
+    int32_t inner_step;          // inner-dim elements per box
+    int32_t swizzle;             // 0: none, 1: 128-byte
+    uint8_t cdim[TMA_MAXRANK];   // tensor-map dim i -> canonical dim
+    uint8_t pad_[3];
+    int32_t box[TMA_MAXRANK];    // box extent per tensor-map dim
+    // consumer functional: dense byte offset per OUTPUT-order slot
+    int32_t d_lo[MAXTD];
+    int32_t inner_slot;          // output-order slot of this operand's inner dim (-1: not a tile dim)
+    int32_t split_bits;          // inner coordinate bits that stay inside one box row
+    int32_t d_hi;                // byte stride of the box index
+    int32_t s_joff[MAXEPT];      // (swizzled) j part
+};
+struct TmaParams {
+    int32_t nin;
+    int32_t nstage;
+    int32_t stage_bytes;
+    int32_t pad_;
+    TmaOperand op[TMA_MAXIN];
+};
+SB_HD uint32_t swizzle128(uint32_t d) { return d ^ (((d >> 7) & 7u) << 4); }
+
 // ---- reduce plan ------------------------------------------------------------------------------------
 struct ReduceParams {
     int32_t ndim, nops, ntd;

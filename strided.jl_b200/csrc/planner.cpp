@@ -1,6 +1,7 @@
 // planner.cpp -- see planner.hpp.  Pure host C++ (no CUDA): unit-tested on CPU through sb_plan_describe and
 // through the thread-grid emulator in tests/emul/.
 #include "planner.hpp"
+#include "tma_tile.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -609,6 +610,130 @@ bool build_tile_order(const Canon &c, const MapParams &P, std::vector<int32_t> &
     return true;
 }
 
+// ---- TMA-staged variant ------------------------------------------------------------------------------------
+bool tma_instantiated(int ct, int recipe, int nin_t, int ept)
+{
+    if (ept != 8) return false;
+    if (ct == C32) return (recipe == RC_COPY && nin_t == 1) || (recipe == RC_INTERP && (nin_t == 1 || nin_t == 2));
+    if (ct != F32 && ct != F64) return false;
+    switch (recipe) {
+    case RC_COPY: case RC_SCALE: return nin_t == 1;
+    case RC_ADD2: case RC_ADD2_MUL: case RC_ADD2_DIV: case RC_AXPY: case RC_AXPBY: return nin_t == 2;
+    case RC_INTERP: return nin_t == 1 || nin_t == 2 || nin_t == 4;
+    default: return false;
+    }
+}
+
+// Fills plan.tma / plan.tma_global when every input tile of the map plan P can be fetched by the TMA unit.
+bool plan_tma(const Canon &c, const MapParams &P, const int *tdim, Plan &plan)
+{
+    if (std::getenv("SB_NO_TMA")) return false;
+    const int n = c.ndim, nin = c.nops - 1, esz = dtype_size(c.ct);
+    if (P.nstaged < 1 || !P.uniform || nin < 1 || nin > TMA_MAXIN || n > TMA_MAXRANK) return false;
+    if (!tma_instantiated(plan.key.ct, plan.key.recipe, plan.key.nin, plan.key.ept)) return false;
+    for (int d = 0; d < n; ++d)
+        if (P.tile_b[d] > 256 || c.dims[d] >= ((int64_t)1 << 31)) return false;
+    TmaParams T;
+    std::memset(&T, 0, sizeof T);
+    T.nin = nin;
+    int32_t off = 0;
+    const OrderTab &oo = P.order[0];
+    for (int k = 1; k <= nin; ++k) {
+        TmaOperand &o = T.op[k - 1];
+        Plan::TmaGlobal &g = plan.tma_global[k - 1];
+        g = Plan::TmaGlobal{};
+        int ord[MAXD];
+        for (int d = 0; d < n; ++d) {
+            if (c.strides[k][d] <= 0) return false;
+            ord[d] = d;
+        }
+        std::stable_sort(ord, ord + n, [&](int a, int b) { return c.strides[k][a] < c.strides[k][b]; });
+        if (c.strides[k][ord[0]] != 1) return false;
+        o.rank = n;
+        g.rank = n;
+        g.elem_bytes = esz;
+        int64_t rows = 1;
+        for (int i = 0; i < n; ++i) {
+            const int d = ord[i];
+            o.cdim[i] = (uint8_t)d;
+            o.box[i] = P.tile_b[d];
+            g.gdim[i] = (uint64_t)c.dims[d];
+            g.gstride_bytes[i] = (uint64_t)c.strides[k][d] * (uint64_t)esz;
+            if (i > 0) {
+                if (g.gstride_bytes[i] % 16 != 0 || g.gstride_bytes[i] >= ((uint64_t)1 << 40)) return false;
+                rows *= P.tile_b[d];
+            }
+        }
+        const int b = P.tile_b[ord[0]];
+        if (P.staged[k]) {
+            const int ipb = 128 / esz;
+            if (b < ipb || b % ipb != 0 || rows < 8) return false;
+            o.swizzle = 1;
+            o.nbox = b / ipb;
+            o.inner_step = ipb;
+            o.box[0] = ipb;
+            o.box_bytes = (int32_t)(128 * rows);
+        } else {
+            if ((b * esz) % 16 != 0 || b * esz < 16) return false;
+            // a direct operand is read in output order: its inner dim must be the output's fastest tile dim
+            if (ord[0] != tdim[oo.td[0]]) return false;
+            o.swizzle = 0;
+            o.nbox = 1;
+            o.inner_step = b;
+            o.box_bytes = (int32_t)(rows * b * esz);
+        }
+        g.swizzle = o.swizzle;
+        for (int i = 0; i < n; ++i) g.box[i] = (uint32_t)o.box[i];
+        o.smem_off = off;
+        off += ((o.box_bytes * o.nbox) + 1023) & ~1023;
+        // consumer functional per OUTPUT-order slot
+        o.inner_slot = -1;
+        o.split_bits = 0;
+        o.d_hi = 0;
+        for (int s = 0; s < oo.n; ++s) {
+            const int cd = tdim[oo.td[s]];
+            int i = 0;
+            while (i < n && ord[i] != cd) ++i;
+            if (i == n) return false;
+            if (o.swizzle) {
+                if (i == 0) {
+                    o.d_lo[s] = esz;
+                    o.inner_slot = s;
+                    o.split_bits = ilog2_ceil(o.inner_step);
+                    o.d_hi = o.box_bytes;
+                } else {
+                    int64_t st = 128;
+                    for (int q = 1; q < i; ++q) st *= o.box[q];
+                    o.d_lo[s] = (int32_t)st;
+                }
+            } else {
+                int64_t st = esz;
+                for (int q = 0; q < i; ++q) st *= o.box[q];
+                o.d_lo[s] = (int32_t)st;
+            }
+        }
+        for (int j = 0; j < P.ept; ++j) {
+            uint32_t d = 0;
+            for (int s = 0; s < oo.n; ++s) d += tma_slot_offset(o, s, field_of(oo, s, j * THREADS));
+            o.s_joff[j] = (int32_t)(o.swizzle ? swizzle128(d) : d);
+        }
+    }
+    T.stage_bytes = off;
+    int ns = (int)(98304 / std::max(1, off));
+    if (ns < 2) return false;
+    if (ns > 4) ns = 4;
+    if (const char *e = std::getenv("SB_TMA_STAGES")) {
+        const int v = std::atoi(e);
+        if (v >= 2 && v <= 8) ns = v;
+    }
+    T.nstage = ns;
+    plan.tma = T;
+    plan.tma_smem_bytes = (int64_t)ns * off + 1024;
+    if (plan.tma_smem_bytes > 220 * 1024) return false;
+    plan.tma_ok = true;
+    return true;
+}
+
 int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err)
 {
     MapParams &P = plan.map;
@@ -779,6 +904,7 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
     if (plan.smem_bytes > 200 * 1024) { err = "staging buffers exceed shared memory"; return SB_E_UNSUPPORTED; }
     plan.grid = std::min<int64_t>(P.ntiles, (int64_t)dev.sm_count * dev.ctas_per_sm);
     if (build_tile_order(c, P, plan.tile_order)) plan.note = "alias-aware tile order";
+    plan_tma(c, P, tdim, plan);
     plan.elements = 1;
     for (int i = 0; i < n; ++i) plan.elements *= c.dims[i];
     return SB_OK;
@@ -1018,7 +1144,7 @@ std::string describe_plan(const Plan &p)
         const MapParams &P = p.map;
         arr64("dims", P.dims, P.ndim);
         arr32("tile", P.tile_b, P.ndim);
-        os << ",\"ntiles\":" << P.ntiles << ",\"tile_order\":" << (p.tile_order.empty() ? 0 : 1) << ",\"nstaged\":" << P.nstaged << ",\"staged\":[";
+        os << ",\"ntiles\":" << P.ntiles << ",\"tile_order\":" << (p.tile_order.empty() ? 0 : 1) << ",\"tma\":" << (p.tma_ok ? p.tma.nstage : 0) << ",\"nstaged\":" << P.nstaged << ",\"staged\":[";
         for (int k = 0; k < P.nops; ++k) os << (k ? "," : "") << (int)P.staged[k];
         os << "],\"strides\":[";
         for (int k = 0; k < P.nops; ++k) {

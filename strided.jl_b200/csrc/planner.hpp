@@ -41,6 +41,16 @@ struct Plan {
     int base_src[MAXO] = {0, 1, 2, 3, 4, 5, 6, 7}; // canonical operand k reads sb_desc::base[base_src[k]]
     // optional alias-aware tile order (host copy; uploaded by the ctx)
     std::vector<int32_t> tile_order; // launch position -> tile id (empty: natural order)
+    // TMA-pipelined variant of the same map plan (chosen at bind time when the input bases are 16-byte aligned)
+    bool tma_ok = false;
+    TmaParams tma{};
+    struct TmaGlobal { // what cuTensorMapEncodeTiled needs, minus the base address
+        int rank = 0, elem_bytes = 0, swizzle = 0;
+        uint64_t gdim[TMA_MAXRANK] = {0};
+        uint64_t gstride_bytes[TMA_MAXRANK] = {0}; // entry i is the stride of dim i (entry 0 unused)
+        uint32_t box[TMA_MAXRANK] = {0};
+    } tma_global[TMA_MAXIN];
+    int64_t tma_smem_bytes = 0;
     std::string note;
 };
 

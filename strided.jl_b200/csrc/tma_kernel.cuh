@@ -1,0 +1,185 @@
+// tma_kernel.cuh -- sm_100a kernel: TMA-fed, mbarrier-pipelined strided map (the permutedims / transpose /
+// `(A .+ A') ./ 2` fast path).  SASS evidence: UTMALDG (cp.async.bulk.tensor) + SYNCS (mbarrier).
+//
+// Pipeline (no warp specialisation needed: the math is a few instructions per element):
+//   thread 0 keeps tiles it, it+1, .., it+nstage-2 in flight: for each it issues, per input operand, one
+//   cp.async.bulk.tensor per box into stage (it % nstage), completing on that stage's mbarrier
+//   (expect_tx = stage bytes);  all 256 threads wait on the stage's mbarrier (parity (it / nstage) & 1),
+//   read their EPT elements per operand from shared memory in OUTPUT order (XOR-swizzled addresses), evaluate
+//   f, store with streaming stores;  one __syncthreads per tile hands the stage back to the producer.
+#pragma once
+#include "kernels.cuh"
+#include "tma_tile.hpp"
+#include <cuda.h>
+
+namespace sb {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) __trap(); // a lost TMA transaction must not hang the GPU
+    }
+}
+
+template <int RANK> __device__ __forceinline__ void tma_load(uint32_t dst, const CUtensorMap *map, uint32_t bar, const int32_t *c);
+template <> __device__ __forceinline__ void tma_load<1>(uint32_t dst, const CUtensorMap *map, uint32_t bar, const int32_t *c)
+{
+    asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c[0])
+                 : "memory");
+}
+template <> __device__ __forceinline__ void tma_load<2>(uint32_t dst, const CUtensorMap *map, uint32_t bar, const int32_t *c)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c[0]), "r"(c[1])
+                 : "memory");
+}
+template <> __device__ __forceinline__ void tma_load<3>(uint32_t dst, const CUtensorMap *map, uint32_t bar, const int32_t *c)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c[0]), "r"(c[1]), "r"(c[2])
+                 : "memory");
+}
+template <> __device__ __forceinline__ void tma_load<4>(uint32_t dst, const CUtensorMap *map, uint32_t bar, const int32_t *c)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3])
+                 : "memory");
+}
+template <> __device__ __forceinline__ void tma_load<5>(uint32_t dst, const CUtensorMap *map, uint32_t bar, const int32_t *c)
+{
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4])
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_issue_tile(const MapParams &P, const TmaParams &T, const CUtensorMap *const *maps, uint32_t pos,
+                                               uint32_t stage_base, uint32_t bar)
+{
+    const uint32_t id = P.tile_order ? (uint32_t)P.tile_order[pos] : pos;
+    mbar_expect_tx(bar, (uint32_t)T.stage_bytes);
+    for (int k = 0; k < T.nin; ++k) {
+        const TmaOperand &o = T.op[k];
+        for (int q = 0; q < o.nbox; ++q) {
+            int32_t crd[TMA_MAXRANK];
+            tma_box_coords(P, o, id, q, crd);
+            const uint32_t dst = stage_base + (uint32_t)o.smem_off + (uint32_t)(q * o.box_bytes);
+            switch (o.rank) {
+            case 1: tma_load<1>(dst, maps[k], bar, crd); break;
+            case 2: tma_load<2>(dst, maps[k], bar, crd); break;
+            case 3: tma_load<3>(dst, maps[k], bar, crd); break;
+            case 4: tma_load<4>(dst, maps[k], bar, crd); break;
+            default: tma_load<5>(dst, maps[k], bar, crd); break;
+            }
+        }
+    }
+}
+
+constexpr int TMA_MAXSTAGE = 8;
+
+template <class CT, int RC, int NIN, int EPT>
+__global__ void __launch_bounds__(THREADS, 2)
+map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaParams T, const __grid_constant__ CUtensorMap m0,
+               const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2, const __grid_constant__ CUtensorMap m3)
+{
+    extern __shared__ unsigned char sb_tma_smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[TMA_MAXSTAGE];
+    // stage ring, 1024-byte aligned (the 128-byte swizzle pattern is a function of address bits [4,10))
+    unsigned char *ring = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(sb_tma_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t ring_u32 = smem_u32(ring);
+    const int t = threadIdx.x;
+    const int S = T.nstage;
+    const CUtensorMap *maps[TMA_MAXIN] = {&m0, &m1, &m2, &m3};
+    if (t == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(smem_u32(&full_bar[s]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t ntiles = (uint32_t)P.ntiles;
+    const uint32_t grid = gridDim.x;
+    if (t == 0) { // prologue: S-1 tiles in flight
+        for (int it = 0; it < S - 1; ++it) {
+            const uint32_t pos = blockIdx.x + (uint32_t)it * grid;
+            if (pos < ntiles) tma_issue_tile(P, T, maps, pos, ring_u32 + (uint32_t)(it * T.stage_bytes), smem_u32(&full_bar[it]));
+        }
+    }
+    MapThread<1> th0;
+    map_thread_init<1>(P, t, th0);
+    TmaThread<NIN> th;
+    tma_thread_init<NIN>(P, T, t, th);
+    uint32_t it = 0;
+    int stage = 0;
+    uint32_t parity = 0;
+    for (uint32_t pos = blockIdx.x; pos < ntiles; pos += grid, ++it) {
+        if (t == 0) { // refill the stage that was consumed in the previous iteration
+            const uint32_t ahead = pos + (uint32_t)(S - 1) * grid;
+            int ps = stage + S - 1;
+            if (ps >= S) ps -= S;
+            if (ahead < ntiles && ahead >= pos) tma_issue_tile(P, T, maps, ahead, ring_u32 + (uint32_t)(ps * T.stage_bytes), smem_u32(&full_bar[ps]));
+        }
+        MapTile<1> tl;
+        map_tile_init<1>(P, th0, pos, tl);
+        mbar_wait(smem_u32(&full_bar[stage]), parity);
+        tma_consume<CT, RC, NIN, EPT>(P, T, th, tl, t, ring + (size_t)stage * T.stage_bytes);
+        __syncthreads(); // every thread is done reading this stage
+        if (++stage == S) {
+            stage = 0;
+            parity ^= 1u;
+        }
+    }
+}
+
+struct TmaEntry {
+    KernelKey key;
+    cudaError_t (*launch)(const MapParams &, const TmaParams &, const CUtensorMap *, int grid, size_t smem, cudaStream_t);
+    cudaError_t (*occupancy)(int *nblocks, size_t smem);
+    const void *func;
+};
+
+template <class CT, int RC, int NIN, int EPT> struct TmaLaunch {
+    static cudaError_t launch(const MapParams &P, const TmaParams &T, const CUtensorMap *maps, int grid, size_t smem, cudaStream_t s)
+    {
+        auto k = map_tma_kernel<CT, RC, NIN, EPT>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k<<<grid, THREADS, smem, s>>>(P, T, maps[0], maps[1], maps[2], maps[3]);
+        return cudaGetLastError();
+    }
+    static cudaError_t occupancy(int *nb, size_t smem)
+    {
+        auto k = map_tma_kernel<CT, RC, NIN, EPT>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, THREADS, smem);
+    }
+    static const void *func() { return (const void *)map_tma_kernel<CT, RC, NIN, EPT>; }
+};
+
+#define SB_TMA_ENTRY(CT, DT, RC, NIN, EPT)                                                                           \
+    TmaEntry { KernelKey{DT, RC, NIN, EPT, 1}, &TmaLaunch<CT, RC, NIN, EPT>::launch, &TmaLaunch<CT, RC, NIN, EPT>::occupancy, \
+               TmaLaunch<CT, RC, NIN, EPT>::func() }
+
+const TmaEntry *tma_table(int *n);
+const TmaEntry *find_tma_kernel(const KernelKey &k);
+
+} // namespace sb

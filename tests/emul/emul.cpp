@@ -8,6 +8,8 @@
 #include "../../strided.jl_b200/csrc/map_tile.hpp"
 #include "../../strided.jl_b200/csrc/reduce_tile.hpp"
 #include "../../strided.jl_b200/csrc/planner.hpp"
+#include "../../strided.jl_b200/csrc/tma_tile.hpp"
+#include <cstdlib>
 
 #include <cstring>
 #include <string>
@@ -35,6 +37,75 @@ template <class CT, int RC, int NIN, int EPT, bool U> static void run_map(const 
             }
             for (int t = 0; t < THREADS; ++t) map_phase2<CT, RC, NIN, EPT, U>(P, th[t], tl[t], t, v[t], smem.data());
         }
+}
+
+// TMA-staged variant: the box copies the Tensor Memory Accelerator would perform (dense box, innermost dim first,
+// out-of-bounds elements zero-filled, 128-byte swizzle on the shared-memory address) are emulated, then the
+// real consumer body runs for every thread.
+template <class CT, int RC, int NIN, int EPT> static void run_tma(const Plan &plan, int grid)
+{
+    const MapParams &P = plan.map;
+    const TmaParams &T = plan.tma;
+    std::vector<unsigned char> raw((size_t)T.stage_bytes + 2048);
+    unsigned char *stage = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(raw.data()) + 1023) & ~(uintptr_t)1023);
+    std::vector<MapThread<1>> th0(THREADS);
+    std::vector<TmaThread<NIN>> th(THREADS);
+    for (int t = 0; t < THREADS; ++t) {
+        map_thread_init<1>(P, t, th0[t]);
+        tma_thread_init<NIN>(P, T, t, th[t]);
+    }
+    for (int b = 0; b < grid; ++b)
+        for (uint32_t pos = (uint32_t)b; pos < (uint32_t)P.ntiles; pos += (uint32_t)grid) {
+            const uint32_t id = P.tile_order ? (uint32_t)P.tile_order[pos] : pos;
+            std::memset(stage, 0xCD, (size_t)T.stage_bytes);
+            for (int k = 0; k < T.nin; ++k) {
+                const TmaOperand &o = T.op[k];
+                const Plan::TmaGlobal &g = plan.tma_global[k];
+                const unsigned char *base = P.base[k + 1];
+                for (int q = 0; q < o.nbox; ++q) {
+                    int32_t crd[TMA_MAXRANK];
+                    tma_box_coords(P, o, id, q, crd);
+                    int64_t nelem = 1;
+                    for (int i = 0; i < o.rank; ++i) nelem *= o.box[i];
+                    for (int64_t e = 0; e < nelem; ++e) {
+                        int64_t rest = e, src = 0;
+                        bool oob = false;
+                        for (int i = 0; i < o.rank; ++i) {
+                            const int64_t ix = rest % o.box[i];
+                            rest /= o.box[i];
+                            const int64_t gi = (int64_t)crd[i] + ix;
+                            if (gi < 0 || gi >= (int64_t)g.gdim[i]) oob = true;
+                            src += gi * (i == 0 ? (int64_t)g.elem_bytes : (int64_t)g.gstride_bytes[i]);
+                        }
+                        uint32_t dense = (uint32_t)(e * g.elem_bytes);
+                        uint32_t off = (uint32_t)o.smem_off + (uint32_t)(q * o.box_bytes) + dense;
+                        if (o.swizzle) off = swizzle128(off);
+                        if (oob) std::memset(stage + off, 0, (size_t)g.elem_bytes);
+                        else std::memcpy(stage + off, base + src, (size_t)g.elem_bytes);
+                    }
+                }
+            }
+            for (int t = 0; t < THREADS; ++t) {
+                MapTile<1> tl;
+                map_tile_init<1>(P, th0[t], pos, tl);
+                tma_consume<CT, RC, NIN, EPT>(P, T, th[t], tl, t, stage);
+            }
+        }
+}
+
+template <class CT> static bool tma_dispatch(const Plan &plan, int grid)
+{
+    const KernelKey &k = plan.key;
+    if (k.ept != 8) return false;
+#define TRYT(R, N)                                                                                                   \
+    if (k.recipe == R && k.nin == N) {                                                                               \
+        run_tma<CT, R, N, 8>(plan, grid);                                                                            \
+        return true;                                                                                                 \
+    }
+    TRYT(RC_COPY, 1) TRYT(RC_SCALE, 1) TRYT(RC_ADD2, 2) TRYT(RC_ADD2_MUL, 2) TRYT(RC_ADD2_DIV, 2) TRYT(RC_AXPY, 2) TRYT(RC_AXPBY, 2)
+    TRYT(RC_INTERP, 1) TRYT(RC_INTERP, 2) TRYT(RC_INTERP, 4)
+#undef TRYT
+    return false;
 }
 
 template <class AT, int RC, int NIN, int EPT, bool U> static void run_reduce(const Plan &plan)
@@ -144,6 +215,19 @@ extern "C" int emul_mapreduce(const sb_desc *desc, int grid_limit)
     if (plan.kind == PLAN_MAP) {
         int grid = (int)plan.grid;
         if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;
+        if (plan.tma_ok && !std::getenv("SB_EMUL_NO_TMA")) {
+            bool aligned = true;
+            for (int k = 1; k < plan.map.nops; ++k) aligned = aligned && ((reinterpret_cast<uintptr_t>(plan.map.base[k]) & 15u) == 0);
+            if (aligned) {
+                switch (plan.key.ct) {
+                case F32: ok = tma_dispatch<float>(plan, grid); break;
+                case F64: ok = tma_dispatch<double>(plan, grid); break;
+                case C32: ok = tma_dispatch<cx<float>>(plan, grid); break;
+                default: ok = false; break;
+                }
+                if (ok) return SB_OK;
+            }
+        }
         switch (plan.key.ct) {
         case F32: ok = map_dispatch<float>(plan, grid); break;
         case F64: ok = map_dispatch<double>(plan, grid); break;
