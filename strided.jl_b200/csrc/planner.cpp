@@ -718,6 +718,9 @@ bool plan_tma(const Canon &c, const MapParams &P, const int *tdim, Plan &plan)
             o.s_joff[j] = (int32_t)(o.swizzle ? swizzle128(d) : d);
         }
     }
+    int nboxes = 0;
+    for (int k = 0; k < nin; ++k) nboxes += T.op[k].nbox;
+    if (nboxes > 32) return false; // one producer lane per box
     T.stage_bytes = off;
     int ns = (int)(98304 / std::max(1, off));
     if (ns < 2) return false;

@@ -73,78 +73,124 @@ template <> __device__ __forceinline__ void tma_load<5>(uint32_t dst, const CUte
                  : "memory");
 }
 
-__device__ __forceinline__ void tma_issue_tile(const MapParams &P, const TmaParams &T, const CUtensorMap *const *maps, uint32_t pos,
-                                               uint32_t stage_base, uint32_t bar)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
-    const uint32_t id = P.tile_order ? (uint32_t)P.tile_order[pos] : pos;
-    mbar_expect_tx(bar, (uint32_t)T.stage_bytes);
-    for (int k = 0; k < T.nin; ++k) {
-        const TmaOperand &o = T.op[k];
-        for (int q = 0; q < o.nbox; ++q) {
-            int32_t crd[TMA_MAXRANK];
-            tma_box_coords(P, o, id, q, crd);
-            const uint32_t dst = stage_base + (uint32_t)o.smem_off + (uint32_t)(q * o.box_bytes);
-            switch (o.rank) {
-            case 1: tma_load<1>(dst, maps[k], bar, crd); break;
-            case 2: tma_load<2>(dst, maps[k], bar, crd); break;
-            case 3: tma_load<3>(dst, maps[k], bar, crd); break;
-            case 4: tma_load<4>(dst, maps[k], bar, crd); break;
-            default: tma_load<5>(dst, maps[k], bar, crd); break;
-            }
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// one lane of the producer warp = one box of one operand: decode the tile, build the box coordinates, issue
+__device__ __forceinline__ void tma_issue_box(const MapParams &P, const TmaOperand &o, const CUtensorMap *map, int q, uint32_t id,
+                                              uint32_t dst, uint32_t bar)
+{
+    int32_t crd[TMA_MAXRANK] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < TMA_MAXRANK; ++d) { // canonical ndim <= TMA_MAXRANK on this path
+        if (d < P.ndim) {
+            uint32_t qq, c;
+            fast_divmod(P.tdiv[d], id, qq, c);
+            id = qq;
+            const int32_t origin = (int32_t)c * P.tile_b[d];
+#pragma unroll
+            for (int i = 0; i < TMA_MAXRANK; ++i)
+                if (o.cdim[i] == d && i < o.rank) crd[i] = origin;
         }
+    }
+    crd[0] += q * o.inner_step;
+    switch (o.rank) {
+    case 1: tma_load<1>(dst, map, bar, crd); break;
+    case 2: tma_load<2>(dst, map, bar, crd); break;
+    case 3: tma_load<3>(dst, map, bar, crd); break;
+    case 4: tma_load<4>(dst, map, bar, crd); break;
+    default: tma_load<5>(dst, map, bar, crd); break;
     }
 }
 
 constexpr int TMA_MAXSTAGE = 8;
+constexpr int TMA_THREADS = THREADS + 32;
+#ifndef SB_TMA_MINB
+#define SB_TMA_MINB 3
+#endif // 8 consumer warps + 1 producer warp
 
+// Warp-specialised pipeline:
+//   producer warp : for every tile of this CTA, wait until the stage is free (empty barrier), arm the full
+//                   barrier with the stage's byte count, then each lane issues the cp.async.bulk.tensor of "its"
+//                   (operand, box);
+//   consumer warps: wait on the full barrier, read the tile from shared memory in OUTPUT order, evaluate f, store,
+//                   then release the stage (one arrive per warp on the empty barrier).
+// No CTA-wide barrier in the loop: the producer runs up to `nstage` tiles ahead of the slowest consumer warp.
 template <class CT, int RC, int NIN, int EPT>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(TMA_THREADS, SB_TMA_MINB)
 map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaParams T, const __grid_constant__ CUtensorMap m0,
                const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2, const __grid_constant__ CUtensorMap m3)
 {
     extern __shared__ unsigned char sb_tma_smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[TMA_MAXSTAGE];
+    __shared__ __align__(8) uint64_t empty_bar[TMA_MAXSTAGE];
     // stage ring, 1024-byte aligned (the 128-byte swizzle pattern is a function of address bits [4,10))
     unsigned char *ring = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(sb_tma_smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t ring_u32 = smem_u32(ring);
-    const int t = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = T.nstage;
-    const CUtensorMap *maps[TMA_MAXIN] = {&m0, &m1, &m2, &m3};
-    if (t == 0) {
-        for (int s = 0; s < S; ++s) mbar_init(smem_u32(&full_bar[s]), 1);
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), THREADS / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const uint32_t ntiles = (uint32_t)P.ntiles;
     const uint32_t grid = gridDim.x;
-    if (t == 0) { // prologue: S-1 tiles in flight
-        for (int it = 0; it < S - 1; ++it) {
-            const uint32_t pos = blockIdx.x + (uint32_t)it * grid;
-            if (pos < ntiles) tma_issue_tile(P, T, maps, pos, ring_u32 + (uint32_t)(it * T.stage_bytes), smem_u32(&full_bar[it]));
+    if (warp == THREADS / 32) {
+        // ---------------- producer warp ----------------
+        int bk = -1, bq = 0; // this lane's (operand, box)
+        {
+            int c = 0;
+            for (int k = 0; k < T.nin; ++k)
+                for (int q = 0; q < T.op[k].nbox; ++q, ++c)
+                    if (c == lane) {
+                        bk = k;
+                        bq = q;
+                    }
         }
-    }
-    MapThread<1> th0;
-    map_thread_init<1>(P, t, th0);
-    TmaThread<NIN> th;
-    tma_thread_init<NIN>(P, T, t, th);
-    uint32_t it = 0;
-    int stage = 0;
-    uint32_t parity = 0;
-    for (uint32_t pos = blockIdx.x; pos < ntiles; pos += grid, ++it) {
-        if (t == 0) { // refill the stage that was consumed in the previous iteration
-            const uint32_t ahead = pos + (uint32_t)(S - 1) * grid;
-            int ps = stage + S - 1;
-            if (ps >= S) ps -= S;
-            if (ahead < ntiles && ahead >= pos) tma_issue_tile(P, T, maps, ahead, ring_u32 + (uint32_t)(ps * T.stage_bytes), smem_u32(&full_bar[ps]));
+        const CUtensorMap *map = bk == 0 ? &m0 : bk == 1 ? &m1 : bk == 2 ? &m2 : &m3;
+        const uint32_t box_dst = bk >= 0 ? (uint32_t)T.op[bk].smem_off + (uint32_t)(bq * T.op[bk].box_bytes) : 0u;
+        int stage = 0;
+        uint32_t parity = 1; // a fresh barrier passes a wait on parity 1: every stage starts out empty
+        for (uint32_t pos = blockIdx.x; pos < ntiles; pos += grid) {
+            mbar_wait(smem_u32(&empty_bar[stage]), parity);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            if (lane == 0) mbar_expect_tx(fb, (uint32_t)T.stage_bytes);
+            __syncwarp();
+            if (bk >= 0) {
+                const uint32_t id = P.tile_order ? (uint32_t)P.tile_order[pos] : pos;
+                tma_issue_box(P, T.op[bk], map, bq, id, ring_u32 + (uint32_t)(stage * T.stage_bytes) + box_dst, fb);
+            }
+            if (++stage == S) {
+                stage = 0;
+                parity ^= 1u;
+            }
         }
-        MapTile<1> tl;
-        map_tile_init<1>(P, th0, pos, tl);
-        mbar_wait(smem_u32(&full_bar[stage]), parity);
-        tma_consume<CT, RC, NIN, EPT>(P, T, th, tl, t, ring + (size_t)stage * T.stage_bytes);
-        __syncthreads(); // every thread is done reading this stage
-        if (++stage == S) {
-            stage = 0;
-            parity ^= 1u;
+    } else {
+        // ---------------- consumer warps ----------------
+        const int t = tid;
+        MapThread<1> th0;
+        map_thread_init<1>(P, t, th0);
+        TmaThread<NIN> th;
+        tma_thread_init<NIN>(P, T, t, th);
+        int stage = 0;
+        uint32_t parity = 0;
+        for (uint32_t pos = blockIdx.x; pos < ntiles; pos += grid) {
+            MapTile<1> tl;
+            map_tile_init<1>(P, th0, pos, tl);
+            mbar_wait(smem_u32(&full_bar[stage]), parity);
+            tma_consume<CT, RC, NIN, EPT>(P, T, th, tl, t, ring + (size_t)stage * T.stage_bytes);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage])); // this warp is done with the stage
+            if (++stage == S) {
+                stage = 0;
+                parity ^= 1u;
+            }
         }
     }
 }
@@ -162,7 +208,7 @@ template <class CT, int RC, int NIN, int EPT> struct TmaLaunch {
         auto k = map_tma_kernel<CT, RC, NIN, EPT>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        k<<<grid, THREADS, smem, s>>>(P, T, maps[0], maps[1], maps[2], maps[3]);
+        k<<<grid, TMA_THREADS, smem, s>>>(P, T, maps[0], maps[1], maps[2], maps[3]);
         return cudaGetLastError();
     }
     static cudaError_t occupancy(int *nb, size_t smem)
@@ -170,7 +216,7 @@ template <class CT, int RC, int NIN, int EPT> struct TmaLaunch {
         auto k = map_tma_kernel<CT, RC, NIN, EPT>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, THREADS, smem);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, TMA_THREADS, smem);
     }
     static const void *func() { return (const void *)map_tma_kernel<CT, RC, NIN, EPT>; }
 };
