@@ -318,6 +318,7 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
         if (k < desc.nops)
             for (int q = k; q >= 0; --q)
                 if (desc.base[q] == desc.base[k]) first = (uintptr_t)q + 1;
+        if (k < desc.nops) first |= ((uintptr_t)desc.base[k] & 15u) << 8; // 16-byte alignment decides the vector / TMA paths
         keyd.base[k] = (void *)first;
     }
     for (int i = keyd.ndim; i < SB_MAX_DIMS; ++i) keyd.dims[i] = 0;

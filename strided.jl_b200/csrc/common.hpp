@@ -149,6 +149,9 @@ struct MapParams {
     uint16_t jfield[MAXO][MAXEPT][MAXTD]; // coordinate bits contributed by j, per order slot
     int32_t ept;
     int32_t uniform; // all dtypes == compute type and no conj flags
+    int32_t vbits;   // log2 of the per-thread vector length V (elements): 16 bytes / sizeof(compute type), or 0
+    uint8_t gvec[MAXO]; // operand k: V consecutive elements of its load traversal are contiguous + 16-B aligned in HBM
+    uint8_t svec[MAXO]; // staged operand k: ... and in its staging buffer (128-bit shared-memory stores)
     Program prog;
 };
 
@@ -225,6 +228,13 @@ struct ReduceParams {
     double init_re, init_im;
     Program prog;
 };
+
+// ---- in-tile linear index of element (t, j) -----------------------------------------------------------------
+// V = 2^vbits consecutive elements of the traversal (16 bytes) belong to the same thread, so that global loads/
+// stores and staging-buffer writes can be 128-bit wherever the operand is contiguous along the traversal's fastest
+// dim:  lin = (j mod V) + V * (t + THREADS * (j div V)).  t-bits and j-bits stay disjoint bit fields of lin.
+SB_HD int lin_t(int t, int vbits) { return t << vbits; }
+SB_HD int lin_j(int j, int vbits) { return (j & ((1 << vbits) - 1)) | ((j >> vbits) << (vbits + LOG_THREADS)); }
 
 // ---- small HD helpers ---------------------------------------------------------------------------------
 SB_HD int field_of(const OrderTab &o, int slot, int lin)

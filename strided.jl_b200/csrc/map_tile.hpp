@@ -40,13 +40,14 @@ template <int NOPS> SB_HD void map_thread_init(const MapParams &P, int t, MapThr
         int32_t w = 0, r = 0;
         if (k < P.nops) {
             const OrderTab &o = P.order[k];
+            const int lt = lin_t(t, P.vbits);
             for (int i = 0; i < o.n; ++i) {
-                const int f = field_of(o, i, t);
+                const int f = field_of(o, i, lt);
                 g += (int64_t)f * P.g_tstr[k][i];
                 w += f * P.w_tstr[k][i];
             }
             const OrderTab &oo = P.order[0];
-            for (int i = 0; i < oo.n; ++i) r += field_of(oo, i, t) * P.r_tstr[k][i];
+            for (int i = 0; i < oo.n; ++i) r += field_of(oo, i, lt) * P.r_tstr[k][i];
         }
         th.g_toff[k] = g;
         th.w_toff[k] = w;
@@ -102,10 +103,26 @@ SB_HD bool map_valid(const MapParams &P, const int32_t (&rem)[MAXTD], int k, int
     const OrderTab &o = P.order[k];
     bool ok = true;
     for (int i = 0; i < o.n; ++i) {
-        const int c = field_of(o, i, t) + (int)P.jfield[k][j][i];
+        const int c = field_of(o, i, lin_t(t, P.vbits)) + (int)P.jfield[k][j][i];
         ok = ok && (c < rem[o.td[i]]);
     }
     return ok;
+}
+
+// 16-byte group of V consecutive elements of a traversal (V = 16 / sizeof(CT); V == 1: no vector path)
+template <class CT> struct VecOf {
+    static constexpr int V = sizeof(CT) >= 16 ? 1 : (int)(16 / sizeof(CT));
+    struct alignas(16) type {
+        CT e[V];
+    };
+};
+template <class CT> SB_HD void store_vec16(unsigned char *p, const typename VecOf<CT>::type &x)
+{
+#if defined(__CUDA_ARCH__)
+    __stcs(reinterpret_cast<float4 *>(p), *reinterpret_cast<const float4 *>(&x)); // streaming: the output is not re-read
+#else
+    *reinterpret_cast<typename VecOf<CT>::type *>(p) = x;
+#endif
 }
 
 // Phase 1.  v[k-1][j] receives input k's element (t, j) in input k's LOAD order.
@@ -113,12 +130,24 @@ template <class CT, int NIN, int EPT, bool UNIFORM>
 SB_HD void map_phase1(const MapParams &P, const MapThread<NIN + 1> &th, const MapTile<NIN + 1> &tl, int t,
                       CT (&v)[NIN][EPT], unsigned char *smem)
 {
+    constexpr int V = VecOf<CT>::V;
+    constexpr bool VEC = UNIFORM && V > 1 && (EPT % V == 0);
+    using vec_t = typename VecOf<CT>::type;
     if (tl.full) {
 #pragma unroll
         for (int k = 1; k <= NIN; ++k) {
             if (k < P.nops) {
+                if (VEC && P.gvec[k]) { // 128-bit loads: V elements contiguous along this operand's traversal
 #pragma unroll
-                for (int j = 0; j < EPT; ++j) v[k - 1][j] = load_elem<CT, UNIFORM>(tl.ptr[k] + P.g_joff[k][j], P.dtype[k], P.conj[k]);
+                    for (int j = 0; j < EPT; j += V) {
+                        const vec_t x = *reinterpret_cast<const vec_t *>(tl.ptr[k] + P.g_joff[k][j]);
+#pragma unroll
+                        for (int u = 0; u < V; ++u) v[k - 1][j + u] = x.e[u];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < EPT; ++j) v[k - 1][j] = load_elem<CT, UNIFORM>(tl.ptr[k] + P.g_joff[k][j], P.dtype[k], P.conj[k]);
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < EPT; ++j) v[k - 1][j] = make<CT>(0.0, 0.0);
@@ -141,8 +170,18 @@ SB_HD void map_phase1(const MapParams &P, const MapThread<NIN + 1> &th, const Ma
     for (int k = 1; k <= NIN; ++k) {
         if (k < P.nops && P.staged[k]) {
             unsigned char *s = smem + P.smem_off[k] + th.w_toff[k];
+            if (VEC && P.svec[k]) {
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) *reinterpret_cast<CT *>(s + P.w_joff[k][j]) = v[k - 1][j];
+                for (int j = 0; j < EPT; j += V) {
+                    vec_t x;
+#pragma unroll
+                    for (int u = 0; u < V; ++u) x.e[u] = v[k - 1][j + u];
+                    *reinterpret_cast<vec_t *>(s + P.w_joff[k][j]) = x;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < EPT; ++j) *reinterpret_cast<CT *>(s + P.w_joff[k][j]) = v[k - 1][j];
+            }
         }
     }
 }
@@ -162,7 +201,22 @@ SB_HD void map_phase2(const MapParams &P, const MapThread<NIN + 1> &th, const Ma
     }
     ElemFn<CT, RC> fn;
     unsigned char *ob = const_cast<unsigned char *>(tl.ptr[0]);
-    if (tl.full) {
+    constexpr int V = VecOf<CT>::V;
+    constexpr bool VEC = UNIFORM && V > 1 && (EPT % V == 0);
+    if (tl.full && VEC && P.gvec[0]) {
+#pragma unroll
+        for (int j = 0; j < EPT; j += V) {
+            typename VecOf<CT>::type x;
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                CT a[NIN];
+#pragma unroll
+                for (int k = 0; k < NIN; ++k) a[k] = v[k][j + u];
+                x.e[u] = fn.template eval<NIN>(P.prog, a);
+            }
+            store_vec16<CT>(ob + P.g_joff[0][j], x);
+        }
+    } else if (tl.full) {
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
             CT a[NIN];

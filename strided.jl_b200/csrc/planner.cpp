@@ -375,23 +375,21 @@ namespace {
 
 // choose padded shared-memory strides (in elements) for a staged operand.
 // own = its load order, out = output order; returns sigma per tile-dim slot and the buffer length.
-int32_t choose_smem_strides(const OrderTab &own, const OrderTab &out, int ntd, const int *tbits, int elem_bytes,
-                            int32_t *sigma)
+int32_t choose_smem_strides(const OrderTab &own, const OrderTab &out, int ntd, int elem_bytes, int vbits, bool vec, int32_t *sigma)
 {
-    const int n = own.n;
+    const int n = own.n, V = 1 << vbits;
     int pads[MAXTD] = {0};
     int bestpads[MAXTD] = {0};
     long best_cost = -1;
     int32_t best_len = 0;
-    const int maxpad = 8;
-    // iterate over all pad vectors (n-1 pads)
+    const int maxpad = 8, unit = vec ? V : 1; // vector stores need every row start on a 16-byte boundary
     const int npad = std::max(0, n - 1);
     long combos = 1;
     for (int i = 0; i < npad; ++i) combos *= (maxpad + 1);
     for (long cidx = 0; cidx < combos; ++cidx) {
         long r = cidx;
         for (int i = 0; i < npad; ++i) {
-            pads[i] = (int)(r % (maxpad + 1));
+            pads[i] = (int)(r % (maxpad + 1)) * unit;
             r /= (maxpad + 1);
         }
         int32_t sg[MAXTD] = {0};
@@ -404,13 +402,14 @@ int32_t choose_smem_strides(const OrderTab &own, const OrderTab &out, int ntd, c
         for (int i = 0; i < n; ++i) len += ((1 << own.bits[i]) - 1) * sg[own.td[i]];
         int32_t wa[32], ra[32];
         for (int l = 0; l < 32; ++l) {
+            const int lin = lin_t(l, vbits);
             int32_t w = 0, rr = 0;
-            for (int i = 0; i < own.n; ++i) w += field_of(own, i, l) * sg[own.td[i]];
-            for (int i = 0; i < out.n; ++i) rr += field_of(out, i, l) * sg[out.td[i]];
-            wa[l] = w;
+            for (int i = 0; i < own.n; ++i) w += field_of(own, i, lin) * sg[own.td[i]];
+            for (int i = 0; i < out.n; ++i) rr += field_of(out, i, lin) * sg[out.td[i]];
+            wa[l] = vec ? w / V : w; // 16-byte units for vector stores
             ra[l] = rr;
         }
-        const long cost = smem_wavefronts(wa, 32, elem_bytes) + smem_wavefronts(ra, 32, elem_bytes);
+        const long cost = smem_wavefronts(wa, 32, vec ? 16 : elem_bytes) + smem_wavefronts(ra, 32, elem_bytes);
         if (best_cost < 0 || cost < best_cost || (cost == best_cost && len < best_len)) {
             best_cost = cost;
             best_len = len;
@@ -423,7 +422,6 @@ int32_t choose_smem_strides(const OrderTab &own, const OrderTab &out, int ntd, c
         sigma[own.td[i]] = cur;
         cur = cur * (1 << own.bits[i]) + (i < npad ? bestpads[i] : 0);
     }
-    (void)tbits;
     return best_len;
 }
 
@@ -477,10 +475,10 @@ bool recipe_instantiated(int ct, int recipe, bool uniform, bool reduce)
     return recipe == RC_SCALE;
 }
 
-void fill_common_tables(const OrderTab &o, int ept, uint16_t (*jfield)[MAXTD])
+void fill_common_tables(const OrderTab &o, int ept, int vbits, uint16_t (*jfield)[MAXTD])
 {
     for (int j = 0; j < ept; ++j)
-        for (int i = 0; i < o.n; ++i) jfield[j][i] = (uint16_t)field_of(o, i, j * THREADS);
+        for (int i = 0; i < o.n; ++i) jfield[j][i] = (uint16_t)field_of(o, i, lin_j(j, vbits));
 }
 
 // ---- alias-aware tile order ------------------------------------------------------------------------------
@@ -714,7 +712,7 @@ bool plan_tma(const Canon &c, const MapParams &P, const int *tdim, Plan &plan)
         }
         for (int j = 0; j < P.ept; ++j) {
             uint32_t d = 0;
-            for (int s = 0; s < oo.n; ++s) d += tma_slot_offset(o, s, field_of(oo, s, j * THREADS));
+            for (int s = 0; s < oo.n; ++s) d += tma_slot_offset(o, s, field_of(oo, s, lin_j(j, P.vbits)));
             o.s_joff[j] = (int32_t)(o.swizzle ? swizzle128(d) : d);
         }
     }
@@ -872,19 +870,36 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
             P.nstaged++;
         }
     }
+    // per-thread vector length: 16 bytes of the compute type when storage == compute type
+    const int V = (uniform && esz < 16 && !std::getenv("SB_NO_VEC")) ? 16 / esz : 1;
+    const int vbits = (V > 1 && ept % V == 0) ? ilog2_ceil(V) : 0;
+    P.vbits = vbits;
+    auto aligned16 = [&](int k) {
+        if (((uintptr_t)c.base[k] & 15u) != 0) return false;
+        for (int i = 0; i < n; ++i)
+            if ((P.tstep[k][i] % 16) != 0) return false;
+        return true;
+    };
     // functionals
     for (int k = 0; k < nops; ++k) {
         const OrderTab &o = P.order[k];
         for (int i = 0; i < o.n; ++i) P.g_tstr[k][i] = c.strides[k][tdim[o.td[i]]] * dtype_size(c.dtype[k]); // bytes
         for (int j = 0; j < ept; ++j) {
             int64_t g = 0;
-            for (int i = 0; i < o.n; ++i) g += (int64_t)field_of(o, i, j * THREADS) * P.g_tstr[k][i];
+            for (int i = 0; i < o.n; ++i) g += (int64_t)field_of(o, i, lin_j(j, vbits)) * P.g_tstr[k][i];
             P.g_joff[k][j] = g;
         }
-        fill_common_tables(o, ept, P.jfield[k]);
+        fill_common_tables(o, ept, vbits, P.jfield[k]);
+        // 128-bit global access: the V elements of a group are contiguous and every group start is 16-byte aligned
+        bool gv = vbits > 0 && o.n > 0 && o.bits[0] >= vbits && c.strides[k][tdim[o.td[0]]] == 1 && aligned16(k);
+        for (int i = 1; i < o.n && gv; ++i)
+            if ((P.g_tstr[k][i] % 16) != 0) gv = false;
+        P.gvec[k] = gv ? 1 : 0;
         if (k > 0 && P.staged[k]) {
             int32_t sigma[MAXTD];
-            const int32_t len = choose_smem_strides(o, P.order[0], ntd, tbits, esz, sigma);
+            const bool sv = vbits > 0 && o.bits[0] >= vbits;
+            const int32_t len = choose_smem_strides(o, P.order[0], ntd, esz, vbits, sv, sigma);
+            P.svec[k] = sv ? 1 : 0;
             P.smem_off[k] = smem_elems * esz; // bytes; staged values are stored as the compute type
             smem_elems += (len + 3) & ~3;
             const OrderTab &oo = P.order[0];
@@ -892,8 +907,8 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
             for (int i = 0; i < oo.n; ++i) P.r_tstr[k][i] = sigma[oo.td[i]] * esz;
             for (int j = 0; j < ept; ++j) {
                 int32_t w = 0, r = 0;
-                for (int i = 0; i < o.n; ++i) w += field_of(o, i, j * THREADS) * P.w_tstr[k][i];
-                for (int i = 0; i < oo.n; ++i) r += field_of(oo, i, j * THREADS) * P.r_tstr[k][i];
+                for (int i = 0; i < o.n; ++i) w += field_of(o, i, lin_j(j, vbits)) * P.w_tstr[k][i];
+                for (int i = 0; i < oo.n; ++i) r += field_of(oo, i, lin_j(j, vbits)) * P.r_tstr[k][i];
                 P.w_joff[k][j] = w;
                 P.r_joff[k][j] = r;
             }
@@ -1003,7 +1018,7 @@ int plan_reduce(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &
             P.g_joff[k][j] = g;
         }
     }
-    fill_common_tables(P.order, ept, P.jfield);
+    fill_common_tables(P.order, ept, 0, P.jfield);
     // in-CTA combine layout
     int kslots[MAXTD], nk = 0;
     int32_t kdense[MAXTD] = {0}, rdense[MAXTD] = {0};

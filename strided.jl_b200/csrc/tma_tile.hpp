@@ -29,7 +29,7 @@ template <int NIN> SB_HD void tma_thread_init(const MapParams &P, const TmaParam
     for (int k = 0; k < NIN; ++k) {
         uint32_t d = 0;
         if (k < T.nin) {
-            for (int i = 0; i < oo.n; ++i) d += tma_slot_offset(T.op[k], i, field_of(oo, i, t));
+            for (int i = 0; i < oo.n; ++i) d += tma_slot_offset(T.op[k], i, field_of(oo, i, lin_t(t, P.vbits)));
             if (T.op[k].swizzle) d = swizzle128(d);
         }
         th.s_t[k] = d;
@@ -41,13 +41,24 @@ template <class CT, int RC, int NIN, int EPT>
 SB_HD void tma_consume(const MapParams &P, const TmaParams &T, const TmaThread<NIN> &th, const MapTile<1> &tl, int t,
                        const unsigned char *stage)
 {
+    constexpr int V = VecOf<CT>::V;
+    constexpr bool VEC = V > 1 && (EPT % V == 0);
     CT v[NIN][EPT];
 #pragma unroll
     for (int k = 0; k < NIN; ++k) {
         if (k < T.nin) {
             const unsigned char *s = stage + T.op[k].smem_off;
+            if (VEC && P.vbits > 0 && !T.op[k].swizzle) { // un-swizzled (direct) operand: 128-bit shared-memory loads
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) v[k][j] = *reinterpret_cast<const CT *>(s + (th.s_t[k] ^ (uint32_t)T.op[k].s_joff[j]));
+                for (int j = 0; j < EPT; j += V) {
+                    const typename VecOf<CT>::type x = *reinterpret_cast<const typename VecOf<CT>::type *>(s + (th.s_t[k] ^ (uint32_t)T.op[k].s_joff[j]));
+#pragma unroll
+                    for (int u = 0; u < V; ++u) v[k][j + u] = x.e[u];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < EPT; ++j) v[k][j] = *reinterpret_cast<const CT *>(s + (th.s_t[k] ^ (uint32_t)T.op[k].s_joff[j]));
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < EPT; ++j) v[k][j] = make<CT>(0.0, 0.0);
@@ -55,7 +66,20 @@ SB_HD void tma_consume(const MapParams &P, const TmaParams &T, const TmaThread<N
     }
     ElemFn<CT, RC> fn;
     unsigned char *ob = const_cast<unsigned char *>(tl.ptr[0]);
-    if (tl.full) {
+    if (tl.full && VEC && P.gvec[0]) {
+#pragma unroll
+        for (int j = 0; j < EPT; j += V) {
+            typename VecOf<CT>::type x;
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                CT a[NIN];
+#pragma unroll
+                for (int k = 0; k < NIN; ++k) a[k] = v[k][j + u];
+                x.e[u] = fn.template eval<NIN>(P.prog, a);
+            }
+            store_vec16<CT>(ob + P.g_joff[0][j], x);
+        }
+    } else if (tl.full) {
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
             CT a[NIN];
