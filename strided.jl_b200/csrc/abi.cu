@@ -552,7 +552,9 @@ extern "C" int sb_mapreduce_host(sb_ctx *ctx, const sb_desc *desc)
         if (e != cudaSuccess) return cuda_fail(ctx, e, "stage d2h");
         ctx->stats.d2h_bytes += s.hi - s.lo;
     }
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "sb_mapreduce_host");
+    if (ctx->sync) { // sync == 0: stream-ordered (H2D, kernel, D2H are all enqueued); the caller syncs with sb_sync
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "sb_mapreduce_host");
+    }
     return SB_OK;
 }

@@ -871,7 +871,10 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
         }
     }
     // per-thread vector length: 16 bytes of the compute type when storage == compute type
-    const int V = (uniform && esz < 16 && !std::getenv("SB_NO_VEC")) ? 16 / esz : 1;
+    // measured (profiles/r01_v4_vector_experiment.txt): 128-bit accesses pay off for all-direct plans and for 4-byte
+    // eltypes; for 8-byte staged plans the extra shared-memory conflicts of the 128-bit path cost more than they save
+    const bool want_vec = (P.nstaged == 0 || esz == 4) && !std::getenv("SB_NO_VEC");
+    const int V = (uniform && esz < 16 && want_vec) ? 16 / esz : 1;
     const int vbits = (V > 1 && ept % V == 0) ? ilog2_ceil(V) : 0;
     P.vbits = vbits;
     auto aligned16 = [&](int k) {

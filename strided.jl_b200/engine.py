@@ -101,8 +101,11 @@ def make_desc(tokens, op, initop, init, dims, views) -> abi.sb_desc:
     return d
 
 
-def run_mapreduce(tokens, op, initop, init, dims, views):
-    """_mapreduce_fuse!(f, op, initop, dims, arrays) on the device (reference src/mapreduce.jl:98-99)."""
+def run_mapreduce(tokens, op, initop, init, dims, views, engine=None):
+    """_mapreduce_fuse!(f, op, initop, dims, arrays) on the device (reference src/mapreduce.jl:98-99).
+
+    `engine`: an explicit :class:`Engine` (its own ctx + stream), e.g. two of them to overlap the H2D of one call
+    with the D2H of the previous one on host-resident operands; default: the per-device engine."""
     desc = make_desc(tokens, op, initop, init, dims, views)
     devs = {v.device for v in views}
     if len(devs) != 1:
@@ -110,11 +113,12 @@ def run_mapreduce(tokens, op, initop, init, dims, views):
     dev = devs.pop()
     if dev.startswith("cuda"):
         idx = int(dev.split(":")[1]) if ":" in dev else torch.cuda.current_device()
-        eng = get_engine(idx)
-        eng.set_stream(torch.cuda.current_stream(idx).cuda_stream)
+        eng = engine or get_engine(idx)
+        if engine is None:
+            eng.set_stream(torch.cuda.current_stream(idx).cuda_stream)
         eng.mapreduce(desc, host=False)
     else:  # host parents (plain `Array`s): staged through the device by sb_mapreduce_host
-        eng = get_engine(0)
+        eng = engine or get_engine(0)
         eng.mapreduce(desc, host=True)
     return views[0]
 

@@ -1,0 +1,72 @@
+"""GPU suite: the sharded (one process per GPU) use of the path with the CUDA engine as the per-rank compute.
+With >= 2 GPUs the ranks are real NCCL ranks; with one GPU the same code runs at world size 1 (no collective)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from helpers import sb
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(rank, world, device):
+    import torch
+    from strided_jl_b200 import sharded
+    g, m = 8, 256
+    rng = np.random.default_rng(1234)
+    full = rng.standard_normal(g * m * m)
+    A3 = full.reshape((g, m, m), order="F")
+    # config-5 placement: every rank holds its slab DENSE in its own HBM
+    lo, hi = sharded.shard_range(g, rank, world)
+    slab = torch.from_numpy(np.ascontiguousarray(A3[lo:hi].reshape(-1, order="F"))).to(device)
+    loc = sb.StridedView(slab, (hi - lo, m, m), (1, hi - lo, (hi - lo) * m))
+    out = sharded.sharded_mapreduce("abs2", "+", loc, dims=(1, 2), shard_dim=0)
+    np.testing.assert_allclose(out.to_numpy().reshape(-1), (A3[lo:hi] ** 2).sum(axis=(1, 2)), rtol=1e-12)
+    # reduced dim sharded -> one all-reduce of g elements
+    lo, hi = sharded.shard_range(m, rank, world)
+    slab2 = torch.from_numpy(np.ascontiguousarray(A3[:, :, lo:hi].reshape(-1, order="F"))).to(device)
+    loc2 = sb.StridedView(slab2, (g, m, hi - lo), (1, g, g * m))
+    out = sharded.sharded_mapreduce("abs2", "+", loc2, dims=(1, 2), shard_dim=2)
+    np.testing.assert_allclose(out.to_numpy().reshape(-1), (A3 ** 2).sum(axis=(1, 2)), rtol=1e-12)
+    # complete reduction -> one all-reduce of ONE element
+    s = sharded.sharded_mapreduce("identity", "+", loc2, shard_dim=2)
+    assert abs(s - full.sum()) < 1e-8
+    assert sharded.sharded_mapreduce("abs", "max", loc2, shard_dim=2) == np.abs(full).max()
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        _check(rank, world, torch.device("cuda", rank))
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, f"{type(e).__name__}: {e}"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_reductions_on_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        _check(0, 1, torch.device("cuda", 0))
+        return
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
