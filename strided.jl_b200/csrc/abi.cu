@@ -312,7 +312,30 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
 {
     // plan cache: everything but the base pointers (the reference re-plans on every call; config 3 is ~2 us
     // of device work, so planning must not be on the critical path)
-    sb_desc keyd = desc;
+    sb_desc keyd;
+    std::memset(&keyd, 0, sizeof keyd); // field-wise copy below: struct padding must not leak into the key
+    keyd.ndim = desc.ndim;
+    keyd.nops = desc.nops;
+    std::memcpy(keyd.dims, desc.dims, sizeof keyd.dims);
+    std::memcpy(keyd.strides, desc.strides, sizeof keyd.strides);
+    std::memcpy(keyd.dtype, desc.dtype, sizeof keyd.dtype);
+    std::memcpy(keyd.conj, desc.conj, sizeof keyd.conj);
+    keyd.ntok = desc.ntok;
+    for (int i = 0; i < desc.ntok && i < SB_MAX_TOKENS; ++i) {
+        keyd.prog[i].kind = desc.prog[i].kind;
+        keyd.prog[i].a = desc.prog[i].a;
+        keyd.prog[i].re = desc.prog[i].re;
+        keyd.prog[i].im = desc.prog[i].im;
+    }
+    keyd.op = desc.op;
+    keyd.initop = desc.initop;
+    keyd.init_re = desc.init_re;
+    keyd.init_im = desc.init_im;
+    if (keyd.ndim < 0 || keyd.ndim > SB_MAX_DIMS || keyd.nops < 1 || keyd.nops > SB_MAX_OPS || keyd.ntok < 0 || keyd.ntok > SB_MAX_TOKENS) {
+        Plan bad;
+        std::string err;
+        return set_err(ctx, build_plan(desc, ctx->dev, bad, err), err); // let the planner produce the status + message
+    }
     for (int k = 0; k < SB_MAX_OPS; ++k) { // keep only the ALIAS pattern of the bases (which operands share a parent pointer)
         uintptr_t first = 0;
         if (k < desc.nops)

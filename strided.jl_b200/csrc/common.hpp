@@ -146,7 +146,14 @@ struct MapParams {
     int32_t r_tstr[MAXO][MAXTD]; // shared-memory byte stride per OUTPUT-order slot
     int32_t r_joff[MAXO][MAXEPT];
     int32_t smem_off[MAXO];      // byte offset of the operand's staging buffer (elements stored as CT)
-    uint16_t jfield[MAXO][MAXEPT][MAXTD]; // coordinate bits contributed by j, per order slot
+    // edge masks: tile coordinates packed into one word, field of tile-dim td at bit cpos[td] with one guard bit on
+    // top; element (t, j) of operand k has packed coordinates c_toff(t) + c_joff[k][j]; it is inside the array iff
+    // ((R | guard) - C) & guard == guard with R = packed (remaining extent - 1).  One subtract per element.
+    uint32_t c_tstr[MAXO][MAXTD]; // 1 << cpos[td] per order slot
+    uint32_t c_joff[MAXO][MAXEPT];
+    uint32_t guard;
+    uint8_t cpos[MAXTD];
+    uint8_t cbits[MAXTD];
     int32_t ept;
     int32_t uniform; // all dtypes == compute type and no conj flags
     int32_t vbits;   // log2 of the per-thread vector length V (elements): 16 bytes / sizeof(compute type), or 0
@@ -213,7 +220,11 @@ struct ReduceParams {
     OrderTab order;              // load order (input 1's fastest-stride order) over ALL tile dims
     int64_t g_tstr[MAXO][MAXTD]; // BYTES
     int64_t g_joff[MAXO][MAXEPT];
-    uint16_t jfield[MAXEPT][MAXTD];
+    uint32_t c_tstr[MAXTD]; // packed edge-mask coordinates (see MapParams)
+    uint32_t c_joff[MAXEPT];
+    uint32_t guard;
+    uint8_t cpos[MAXTD];
+    uint8_t cbits[MAXTD];
     int32_t s_tstr[MAXTD];       // shared-memory slot (elements) of (t, j) for the final in-CTA combine
     int32_t s_joff[MAXEPT];
     int32_t nout_tile;           // outputs per tile  = prod of kept tile extents
@@ -235,6 +246,21 @@ struct ReduceParams {
 // dim:  lin = (j mod V) + V * (t + THREADS * (j div V)).  t-bits and j-bits stay disjoint bit fields of lin.
 SB_HD int lin_t(int t, int vbits) { return t << vbits; }
 SB_HD int lin_j(int j, int vbits) { return (j & ((1 << vbits) - 1)) | ((j >> vbits) << (vbits + LOG_THREADS)); }
+
+// packed "remaining extent - 1" of a tile (R | guard), from the per-tile-dim remaining extents
+SB_HD uint32_t pack_rem(const int32_t *rem, int ntd, const uint8_t *cpos, const uint8_t *cbits, uint32_t guard)
+{
+    uint32_t r = guard;
+    for (int i = 0; i < ntd; ++i) {
+        const int32_t mx = (1 << cbits[i]) - 1;
+        int32_t v = rem[i] - 1;
+        if (v > mx) v = mx;
+        if (v < 0) return 0; // empty: nothing is valid (guard bits cleared)
+        r |= (uint32_t)v << cpos[i];
+    }
+    return r;
+}
+SB_HD bool packed_valid(uint32_t rg, uint32_t c, uint32_t guard) { return ((rg - c) & guard) == guard; }
 
 // ---- small HD helpers ---------------------------------------------------------------------------------
 SB_HD int field_of(const OrderTab &o, int slot, int lin)

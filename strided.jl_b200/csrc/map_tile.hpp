@@ -24,6 +24,7 @@ template <int NOPS> struct MapThread {
     int64_t g_toff[NOPS]; // global BYTE offset contributed by t, operand k (its load order)
     int32_t w_toff[NOPS]; // staging-buffer write byte offset contributed by t (own order)
     int32_t r_toff[NOPS]; // staging-buffer read byte offset contributed by t (output order)
+    uint32_t c_toff[NOPS]; // packed tile coordinates contributed by t (operand k's load order), for edge masks
 };
 
 template <int NOPS> struct MapTile {
@@ -38,6 +39,7 @@ template <int NOPS> SB_HD void map_thread_init(const MapParams &P, int t, MapThr
     for (int k = 0; k < NOPS; ++k) {
         int64_t g = 0;
         int32_t w = 0, r = 0;
+        uint32_t cc = 0;
         if (k < P.nops) {
             const OrderTab &o = P.order[k];
             const int lt = lin_t(t, P.vbits);
@@ -45,6 +47,7 @@ template <int NOPS> SB_HD void map_thread_init(const MapParams &P, int t, MapThr
                 const int f = field_of(o, i, lt);
                 g += (int64_t)f * P.g_tstr[k][i];
                 w += f * P.w_tstr[k][i];
+                cc += (uint32_t)f * P.c_tstr[k][i];
             }
             const OrderTab &oo = P.order[0];
             for (int i = 0; i < oo.n; ++i) r += field_of(oo, i, lt) * P.r_tstr[k][i];
@@ -52,6 +55,7 @@ template <int NOPS> SB_HD void map_thread_init(const MapParams &P, int t, MapThr
         th.g_toff[k] = g;
         th.w_toff[k] = w;
         th.r_toff[k] = r;
+        th.c_toff[k] = cc;
     }
 }
 
@@ -80,8 +84,8 @@ template <int NOPS> SB_HD void map_tile_init(const MapParams &P, const MapThread
     tl.full = full;
 }
 
-// Remaining extent per tile-dim slot -- only needed on edge tiles (slow path, may use local memory).
-SB_HD void map_tile_rem(const MapParams &P, uint32_t id, int32_t (&rem)[MAXTD])
+// Packed remaining extents (R | guard) of tile `id` -- only needed on edge tiles.
+SB_HD uint32_t map_tile_rem(const MapParams &P, uint32_t id)
 {
     int64_t origin[MAXD];
     for (int d = 0; d < P.ndim; ++d) {
@@ -90,23 +94,18 @@ SB_HD void map_tile_rem(const MapParams &P, uint32_t id, int32_t (&rem)[MAXTD])
         id = q;
         origin[d] = (int64_t)c * P.tile_b[d];
     }
-    for (int i = 0; i < MAXTD; ++i) {
-        int64_t r = 1;
-        if (i < P.ntd) r = P.dims[P.tdim[i]] - origin[P.tdim[i]];
+    int32_t rem[MAXTD];
+    for (int i = 0; i < P.ntd; ++i) {
+        const int64_t r = P.dims[P.tdim[i]] - origin[P.tdim[i]];
         rem[i] = r > 0x7fffffff ? 0x7fffffff : (int32_t)r;
     }
+    return pack_rem(rem, P.ntd, P.cpos, P.cbits, P.guard);
 }
 
 // is element (t, j) of operand k's traversal inside the array?  (only evaluated on edge tiles)
-SB_HD bool map_valid(const MapParams &P, const int32_t (&rem)[MAXTD], int k, int t, int j)
+template <int NOPS> SB_HD bool map_valid(const MapParams &P, const MapThread<NOPS> &th, uint32_t rg, int k, int j)
 {
-    const OrderTab &o = P.order[k];
-    bool ok = true;
-    for (int i = 0; i < o.n; ++i) {
-        const int c = field_of(o, i, lin_t(t, P.vbits)) + (int)P.jfield[k][j][i];
-        ok = ok && (c < rem[o.td[i]]);
-    }
-    return ok;
+    return packed_valid(rg, th.c_toff[k] + P.c_joff[k][j], P.guard);
 }
 
 // 16-byte group of V consecutive elements of a traversal (V = 16 / sizeof(CT); V == 1: no vector path)
@@ -154,14 +153,13 @@ SB_HD void map_phase1(const MapParams &P, const MapThread<NIN + 1> &th, const Ma
             }
         }
     } else {
-        int32_t rem[MAXTD];
-        map_tile_rem(P, tl.id, rem);
+        const uint32_t rg = map_tile_rem(P, tl.id);
 #pragma unroll
         for (int k = 1; k <= NIN; ++k) {
 #pragma unroll
             for (int j = 0; j < EPT; ++j) {
                 CT x = make<CT>(0.0, 0.0);
-                if (k < P.nops && map_valid(P, rem, k, t, j)) x = load_elem<CT, UNIFORM>(tl.ptr[k] + P.g_joff[k][j], P.dtype[k], P.conj[k]);
+                if (k < P.nops && map_valid(P, th, rg, k, j)) x = load_elem<CT, UNIFORM>(tl.ptr[k] + P.g_joff[k][j], P.dtype[k], P.conj[k]);
                 v[k - 1][j] = x;
             }
         }
@@ -225,15 +223,14 @@ SB_HD void map_phase2(const MapParams &P, const MapThread<NIN + 1> &th, const Ma
             store_elem<CT, UNIFORM>(ob + P.g_joff[0][j], P.dtype[0], P.conj[0], fn.template eval<NIN>(P.prog, a));
         }
     } else {
-        int32_t rem[MAXTD];
-        map_tile_rem(P, tl.id, rem);
+        const uint32_t rg = map_tile_rem(P, tl.id);
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
             CT a[NIN];
 #pragma unroll
             for (int k = 0; k < NIN; ++k) a[k] = v[k][j];
             const CT r = fn.template eval<NIN>(P.prog, a);
-            if (map_valid(P, rem, 0, t, j)) store_elem<CT, UNIFORM>(ob + P.g_joff[0][j], P.dtype[0], P.conj[0], r);
+            if (map_valid(P, th, rg, 0, j)) store_elem<CT, UNIFORM>(ob + P.g_joff[0][j], P.dtype[0], P.conj[0], r);
         }
     }
 }

@@ -475,10 +475,28 @@ bool recipe_instantiated(int ct, int recipe, bool uniform, bool reduce)
     return recipe == RC_SCALE;
 }
 
-void fill_common_tables(const OrderTab &o, int ept, int vbits, uint16_t (*jfield)[MAXTD])
+// packed edge-mask coordinates: field of tile-dim td at bit cpos[td], one guard bit above each field
+uint32_t fill_cpos(int ntd, const int *tbits, uint8_t *cpos, uint8_t *cbits)
 {
-    for (int j = 0; j < ept; ++j)
-        for (int i = 0; i < o.n; ++i) jfield[j][i] = (uint16_t)field_of(o, i, lin_j(j, vbits));
+    uint32_t guard = 0;
+    int pos = 0;
+    for (int i = 0; i < ntd; ++i) {
+        cpos[i] = (uint8_t)pos;
+        cbits[i] = (uint8_t)tbits[i];
+        pos += tbits[i];
+        guard |= 1u << pos;
+        pos += 1;
+    }
+    return guard;
+}
+void fill_common_tables(const OrderTab &o, int ept, int vbits, const uint8_t *cpos, uint32_t *c_tstr, uint32_t *c_joff)
+{
+    for (int i = 0; i < o.n; ++i) c_tstr[i] = 1u << cpos[o.td[i]];
+    for (int j = 0; j < ept; ++j) {
+        uint32_t c = 0;
+        for (int i = 0; i < o.n; ++i) c += (uint32_t)field_of(o, i, lin_j(j, vbits)) * c_tstr[i];
+        c_joff[j] = c;
+    }
 }
 
 // ---- alias-aware tile order ------------------------------------------------------------------------------
@@ -775,37 +793,86 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
         if (hot[i]) needed <<= std::min(cap[i], minrun_bits);
     int64_t elements = 1;
     for (int i = 0; i < n; ++i) elements *= c.dims[i];
-    const int ept = default_ept(c.ct, P.prog.recipe, template_nin(P.prog.recipe, nin), uniform, needed, elements, dev);
-    const int ebits = LOG_THREADS + ilog2_ceil(ept);
-    int used = 0;
-    // phase 1: a sector-sized run along every hot dim
-    for (int i = 0; i < n && used < ebits; ++i)
-        if (hot[i]) {
-            const int b = std::min(std::min(cap[i], minrun_bits), ebits - used);
-            tb[i] = b;
-            used += b;
-        }
-    // phase 2: grow the hot dim with the shortest run (output dim first on ties)
-    while (used < ebits) {
-        int pick = -1;
-        for (int i = 0; i < n; ++i)
-            if (hot[i] && tb[i] < cap[i] && (pick < 0 || tb[i] < tb[pick])) pick = i;
-        if (pick < 0) break;
-        tb[pick]++;
-        used++;
+    // Tile extents are powers of two; an extent that does not divide the dim wastes masked lanes (profiles/
+    // r01_v5_sweep_before_tilefix.txt: 70^4 ran at 0.18 of peak with 64-wide tiles).  lim[i] = the largest extent whose
+    // padding waste ceil(n/b)*b/n stays <= 1.2 (never below a 32-byte run for hot dims).
+    auto waste_of = [&](int i, int bits) {
+        const int64_t t = (int64_t)1 << bits;
+        return (double)(((c.dims[i] + t - 1) / t) * t) / (double)c.dims[i];
+    };
+    int lim[MAXD];
+    for (int i = 0; i < n; ++i) {
+        const int lo = hot[i] ? std::min(cap[i], minrun_bits) : 0;
+        int bbits = cap[i];
+        while (bbits > lo && waste_of(i, bbits) > 1.2) --bbits;
+        lim[i] = bbits;
     }
-    // phase 3: other dims, in output order
     auto ntile_dims = [&]() {
         int q = 0;
         for (int i = 0; i < n; ++i) q += tb[i] > 0;
         return q;
     };
-    for (int i = 0; i < n && used < ebits; ++i) {
-        if (hot[i] || cap[i] == 0) continue;
-        if (ntile_dims() >= MAXTD) break;
-        const int b = std::min(cap[i], ebits - used);
-        tb[i] = b;
-        used += b;
+    auto fill = [&](int ebits_try) {
+        int used_ = 0;
+        for (int i = 0; i < n; ++i) tb[i] = 0;
+        // phase 1: a sector-sized run along every hot dim
+        for (int i = 0; i < n && used_ < ebits_try; ++i)
+            if (hot[i]) {
+                const int bb = std::min(std::min(cap[i], minrun_bits), ebits_try - used_);
+                tb[i] = bb;
+                used_ += bb;
+            }
+        // phase 2: grow the hot dim with the shortest run (output dim first on ties)
+        while (used_ < ebits_try) {
+            int pick = -1;
+            for (int i = 0; i < n; ++i)
+                if (hot[i] && tb[i] < lim[i] && (pick < 0 || tb[i] < tb[pick])) pick = i;
+            if (pick < 0) break;
+            tb[pick]++;
+            used_++;
+        }
+        // phase 3: other dims, in output order
+        for (int i = 0; i < n && used_ < ebits_try; ++i) {
+            if (hot[i] || lim[i] == 0) continue;
+            if (ntile_dims() >= MAXTD) break;
+            const int bb = std::min(lim[i], ebits_try - used_);
+            tb[i] = bb;
+            used_ += bb;
+        }
+        return used_;
+    };
+    int ept = default_ept(c.ct, P.prog.recipe, template_nin(P.prog.recipe, nin), uniform, needed, elements, dev);
+    if (!std::getenv("SB_FORCE_EPT")) { // prefer the largest tile that can be filled without padding waste
+        int best = ept, best_left = 1 << 30;
+        for (int e = ept; e >= 4; e /= 2) {
+            if (!ept_instantiated(c.ct, P.prog.recipe, template_nin(P.prog.recipe, nin), e, uniform)) continue;
+            const int eb = LOG_THREADS + ilog2_ceil(e);
+            const int left = eb - fill(eb);
+            if (left < best_left) {
+                best_left = left;
+                best = e;
+            }
+            if (left == 0) break;
+        }
+        ept = best;
+    }
+    const int ebits = LOG_THREADS + ilog2_ceil(ept);
+    int used = fill(ebits);
+    // phase 3b: still room -> raise extents towards the full dim, least additional waste first
+    while (used < ebits) {
+        int pick = -1;
+        double pw = 0;
+        for (int i = 0; i < n; ++i) {
+            if (tb[i] >= cap[i] || (tb[i] == 0 && ntile_dims() >= MAXTD)) continue;
+            const double w = waste_of(i, tb[i] + 1) / waste_of(i, tb[i]);
+            if (pick < 0 || w < pw) {
+                pick = i;
+                pw = w;
+            }
+        }
+        if (pick < 0) break;
+        tb[pick]++;
+        used++;
     }
     // phase 4: pad (elements beyond the array are masked)
     if (used < ebits) {
@@ -870,6 +937,7 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
             P.nstaged++;
         }
     }
+    P.guard = fill_cpos(ntd, tbits, P.cpos, P.cbits);
     // per-thread vector length: 16 bytes of the compute type when storage == compute type
     // measured (profiles/r01_v4_vector_experiment.txt): 128-bit accesses pay off for all-direct plans and for 4-byte
     // eltypes; for 8-byte staged plans the extra shared-memory conflicts of the 128-bit path cost more than they save
@@ -892,7 +960,7 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
             for (int i = 0; i < o.n; ++i) g += (int64_t)field_of(o, i, lin_j(j, vbits)) * P.g_tstr[k][i];
             P.g_joff[k][j] = g;
         }
-        fill_common_tables(o, ept, vbits, P.jfield[k]);
+        fill_common_tables(o, ept, vbits, P.cpos, P.c_tstr[k], P.c_joff[k]);
         // 128-bit global access: the V elements of a group are contiguous and every group start is 16-byte aligned
         bool gv = vbits > 0 && o.n > 0 && o.bits[0] >= vbits && c.strides[k][tdim[o.td[0]]] == 1 && aligned16(k);
         for (int i = 1; i < o.n && gv; ++i)
@@ -1021,7 +1089,8 @@ int plan_reduce(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &
             P.g_joff[k][j] = g;
         }
     }
-    fill_common_tables(P.order, ept, 0, P.jfield);
+    P.guard = fill_cpos(ntd, tbits, P.cpos, P.cbits);
+    fill_common_tables(P.order, ept, 0, P.cpos, P.c_tstr, P.c_joff);
     // in-CTA combine layout
     int kslots[MAXTD], nk = 0;
     int32_t kdense[MAXTD] = {0}, rdense[MAXTD] = {0};

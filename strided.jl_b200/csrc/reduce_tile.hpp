@@ -77,8 +77,8 @@ template <int NIN> SB_HD bool red_step_init(const ReduceParams &P, const RedCta<
     return full;
 }
 
-// remaining extents per tile-dim slot for (out_tile, step): edge tiles only (slow path)
-SB_HD void red_rem(const ReduceParams &P, uint32_t out_tile, uint32_t step, int32_t (&rem)[MAXTD])
+// packed remaining extents (R | guard) for (out_tile, step): edge tiles only (slow path)
+SB_HD uint32_t red_rem(const ReduceParams &P, uint32_t out_tile, uint32_t step)
 {
     int64_t origin[MAXD];
     uint32_t id = out_tile;
@@ -89,21 +89,12 @@ SB_HD void red_rem(const ReduceParams &P, uint32_t out_tile, uint32_t step, int3
         id = q;
         origin[d] = (int64_t)cd * P.tile_b[d];
     }
-    for (int i = 0; i < MAXTD; ++i) {
-        int64_t r = 1;
-        if (i < P.ntd) r = P.dims[P.tdim[i]] - origin[P.tdim[i]];
+    int32_t rem[MAXTD];
+    for (int i = 0; i < P.ntd; ++i) {
+        const int64_t r = P.dims[P.tdim[i]] - origin[P.tdim[i]];
         rem[i] = r > 0x7fffffff ? 0x7fffffff : (int32_t)r;
     }
-}
-
-SB_HD bool red_valid(const ReduceParams &P, const int32_t (&rem)[MAXTD], int t, int j)
-{
-    bool ok = true;
-    for (int i = 0; i < P.order.n; ++i) {
-        const int f = field_of(P.order, i, t) + (int)P.jfield[j][i];
-        ok = ok && (f < rem[P.order.td[i]]);
-    }
-    return ok;
+    return pack_rem(rem, P.ntd, P.cpos, P.cbits, P.guard);
 }
 
 // Accumulation phase of one CTA for thread t.  Leaves the EPT accumulators in shared memory.
@@ -115,6 +106,8 @@ SB_HD void red_accumulate(const ReduceParams &P, uint32_t bid, int t, AT *smem)
     AT acc[EPT];
 #pragma unroll
     for (int j = 0; j < EPT; ++j) acc[j] = red_neutral<AT>(P.op);
+    uint32_t c_toff = 0;
+    for (int i = 0; i < P.order.n; ++i) c_toff += (uint32_t)field_of(P.order, i, t) * P.c_tstr[i];
     ElemFn<AT, RC> fn;
     const int64_t s0 = (int64_t)c.split * P.steps_per_split;
     int64_t s1 = s0 + P.steps_per_split;
@@ -139,11 +132,10 @@ SB_HD void red_accumulate(const ReduceParams &P, uint32_t bid, int t, AT *smem)
                 acc[j] = red_apply<AT>(P.op, acc[j], fn.template eval<NIN>(P.prog, a));
             }
         } else {
-            int32_t rem[MAXTD];
-            red_rem(P, c.out_tile, (uint32_t)step, rem);
+            const uint32_t rg = red_rem(P, c.out_tile, (uint32_t)step);
 #pragma unroll
             for (int j = 0; j < EPT; ++j) {
-                if (!red_valid(P, rem, t, j)) continue;
+                if (!packed_valid(rg, c_toff + P.c_joff[j], P.guard)) continue;
                 AT a[NIN];
 #pragma unroll
                 for (int k = 0; k < NIN; ++k)

@@ -184,7 +184,7 @@ map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaP
             MapTile<1> tl;
             map_tile_init<1>(P, th0, pos, tl);
             mbar_wait(smem_u32(&full_bar[stage]), parity);
-            tma_consume<CT, RC, NIN, EPT>(P, T, th, tl, t, ring + (size_t)stage * T.stage_bytes);
+            tma_consume<CT, RC, NIN, EPT>(P, T, th, th0, tl, t, ring + (size_t)stage * T.stage_bytes);
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage])); // this warp is done with the stage
             if (++stage == S) {

@@ -38,7 +38,7 @@ template <int NIN> SB_HD void tma_thread_init(const MapParams &P, const TmaParam
 
 // consume one landed stage: `stage` points at the stage base (1024-byte aligned)
 template <class CT, int RC, int NIN, int EPT>
-SB_HD void tma_consume(const MapParams &P, const TmaParams &T, const TmaThread<NIN> &th, const MapTile<1> &tl, int t,
+SB_HD void tma_consume(const MapParams &P, const TmaParams &T, const TmaThread<NIN> &th, const MapThread<1> &th0, const MapTile<1> &tl, int t,
                        const unsigned char *stage)
 {
     constexpr int V = VecOf<CT>::V;
@@ -88,15 +88,14 @@ SB_HD void tma_consume(const MapParams &P, const TmaParams &T, const TmaThread<N
             store_elem<CT, true>(ob + P.g_joff[0][j], P.dtype[0], 0, fn.template eval<NIN>(P.prog, a));
         }
     } else {
-        int32_t rem[MAXTD];
-        map_tile_rem(P, tl.id, rem);
+        const uint32_t rg = map_tile_rem(P, tl.id);
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
             CT a[NIN];
 #pragma unroll
             for (int k = 0; k < NIN; ++k) a[k] = v[k][j];
             const CT r = fn.template eval<NIN>(P.prog, a);
-            if (map_valid(P, rem, 0, t, j)) store_elem<CT, true>(ob + P.g_joff[0][j], P.dtype[0], 0, r);
+            if (map_valid(P, th0, rg, 0, j)) store_elem<CT, true>(ob + P.g_joff[0][j], P.dtype[0], 0, r);
         }
     }
 }

@@ -88,7 +88,7 @@ template <class CT, int RC, int NIN, int EPT> static void run_tma(const Plan &pl
             for (int t = 0; t < THREADS; ++t) {
                 MapTile<1> tl;
                 map_tile_init<1>(P, th0[t], pos, tl);
-                tma_consume<CT, RC, NIN, EPT>(P, T, th[t], tl, t, stage);
+                tma_consume<CT, RC, NIN, EPT>(P, T, th[t], th0[t], tl, t, stage);
             }
         }
 }
