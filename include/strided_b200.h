@@ -32,6 +32,10 @@
  *   - `conj[k] != 0` <=> the view's `op` is `conj`/`adjoint` on a complex eltype: the element is
  *     conjugated on load, and (operand 0) on store (ParentIndex get/setindex, mapreduce.jl:276-278).
  *
+ * Element functions outside the pre-compiled recipes run either through an in-kernel interpreter or, for problems of
+ * at least SB_JIT_MIN_ELEMENTS elements (default 2^20), through a kernel specialised at run time with NVRTC and
+ * cached on disk (~/.cache/strided_b200); SB_NO_JIT=1 disables the latter.
+ *
  * Error behaviour: no entry point throws or aborts; every one returns an `sb_status`.  The glue maps
  * SB_E_SHAPE -> DimensionMismatch (mapreduce.jl:43-46, broadcast.jl:61), SB_E_UNSUPPORTED -> fall
  * back to the original CPU method, anything else -> ErrorException(sb_last_error(ctx)).
@@ -163,6 +167,7 @@ typedef struct sb_stats {
     uint64_t d2h_bytes;
     uint64_t plans_built;
     uint64_t plans_cached;
+    uint64_t jit_launches; /* launches of NVRTC-specialised kernels (subset of `launches`) */
 } sb_stats;
 int sb_get_stats(sb_ctx *ctx, sb_stats *out);
 int sb_reset_stats(sb_ctx *ctx);

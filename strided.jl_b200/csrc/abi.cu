@@ -3,6 +3,7 @@
 // There is NO CPU execution path here: without a CUDA device every compute entry point returns
 // SB_E_NODEVICE.  (sb_plan_describe is pure host planning and works anywhere.)
 #include "tma_kernel.cuh"
+#include "jit.hpp"
 
 #include <cstdio>
 #include <cstring>
@@ -73,6 +74,12 @@ static bool encode_tma_maps(const Plan &plan, CUtensorMap *maps)
 {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return false;
+    static const CUtensorMapL2promotion l2promo = []() {
+        const char *e = std::getenv("SB_TMA_L2PROMO"); // tuning knob: 0 none, 64, 128 (default), 256
+        const int v = e ? std::atoi(e) : 128;
+        return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+               : v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    }();
     const int nin = plan.tma.nin;
     for (int k = 0; k < nin; ++k) {
         const Plan::TmaGlobal &g = plan.tma_global[k];
@@ -89,7 +96,7 @@ static bool encode_tma_maps(const Plan &plan, CUtensorMap *maps)
         const CUtensorMapDataType dt = g.elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                        : (plan.key.ct == F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_UINT64);
         const CUresult r = enc(&maps[k], dt, (cuuint32_t)g.rank, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               g.swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               g.swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, l2promo,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return false;
     }
@@ -384,6 +391,46 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
     }
     if (plan.kind == PLAN_NOOP) return SB_OK;
     cudaSetDevice(ctx->device);
+    // Run-time specialised element function (NVRTC) instead of the interpreter, once the problem is large enough to
+    // amortise a ~2 s compile (the GPU analog of MINTHREADLENGTH, reference src/mapreduce.jl:141).
+    const JitKernel *jk = nullptr;
+    if (plan.key.recipe == RC_INTERP && jit_enabled()) {
+        static const int64_t jit_min = []() {
+            const char *e = std::getenv("SB_JIT_MIN_ELEMENTS");
+            return e ? (int64_t)std::atoll(e) : ((int64_t)1 << 20);
+        }();
+        const char *e2 = std::getenv("SB_JIT_MIN_ELEMENTS"); // re-read: tests toggle it at run time
+        const int64_t thr = e2 ? (int64_t)std::atoll(e2) : jit_min;
+        if (plan.elements >= thr)
+            jk = jit_get(plan.kind == PLAN_MAP ? JIT_MAP : JIT_REDUCE, plan.key, plan.kind == PLAN_MAP ? plan.map.prog : plan.red.prog);
+    }
+    if (jk && plan.kind == PLAN_MAP) {
+        const void *fn = (const void *)jk->fn;
+        if (plan.smem_bytes > 48 * 1024 && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            jk = nullptr;
+        }
+        if (jk) {
+            int nb = jk->min_blocks;
+            auto okey = std::make_pair(fn, (size_t)plan.smem_bytes);
+            auto oit = ctx->occ.find(okey);
+            if (oit != ctx->occ.end()) nb = oit->second;
+            else {
+                int q = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, fn, THREADS, (size_t)plan.smem_bytes) == cudaSuccess && q > 0) nb = q;
+                else cudaGetLastError();
+                ctx->occ[okey] = nb;
+            }
+            int64_t grid = std::min<int64_t>(plan.map.ntiles, (int64_t)ctx->dev.sm_count * nb);
+            if (grid < 1) grid = 1;
+            void *args[] = {(void *)&plan.map};
+            cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(THREADS), args, (size_t)plan.smem_bytes, ctx->stream);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "jit map launch");
+            ctx->stats.launches++;
+            ctx->stats.jit_launches++;
+            return SB_OK;
+        }
+    }
     if (plan.kind == PLAN_MAP && plan.tma_ok) { // TMA-pipelined variant when the inputs qualify at bind time
         const TmaEntry *tk = find_tma_kernel(plan.key);
         alignas(64) CUtensorMap maps[TMA_MAXIN];
@@ -426,9 +473,16 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
             ctx->scratch_bytes = want;
         }
         plan.red.scratch = (unsigned char *)ctx->scratch;
-        cudaError_t e = k->launch(plan.red, (int)plan.grid, (size_t)plan.smem_bytes, ctx->stream);
+        cudaError_t e;
+        if (jk) {
+            void *args[] = {(void *)&plan.red};
+            e = cudaLaunchKernel((const void *)jk->fn, dim3((unsigned)plan.grid), dim3(THREADS), args, (size_t)plan.smem_bytes, ctx->stream);
+        } else {
+            e = k->launch(plan.red, (int)plan.grid, (size_t)plan.smem_bytes, ctx->stream);
+        }
         if (e != cudaSuccess) return cuda_fail(ctx, e, "reduce_tile launch");
         ctx->stats.launches++;
+        if (jk) ctx->stats.jit_launches++;
         if (plan.finalize_threads > 0) {
             const int64_t g = (plan.finalize_threads + (THREADS / 32) - 1) / (THREADS / 32); // one warp per output
             e = k->finalize(plan.red, (int)g, ctx->stream);

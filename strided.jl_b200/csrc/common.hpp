@@ -11,7 +11,20 @@
 // from the output's, and consumed in the output's order.  This replaces the reference's cache-blocked loop
 // nest `_mapreduce_kernel!` (src/mapreduce.jl:229-425) and its task bisection (:195-227).
 #pragma once
+#if defined(__CUDACC_RTC__) // NVRTC (csrc/jit.cu): no libc headers
+#include <cuda/std/cstdint>
+using cuda::std::int8_t;
+using cuda::std::int16_t;
+using cuda::std::int32_t;
+using cuda::std::int64_t;
+using cuda::std::uint8_t;
+using cuda::std::uint16_t;
+using cuda::std::uint32_t;
+using cuda::std::uint64_t;
+using cuda::std::uintptr_t;
+#else
 #include <stdint.h>
+#endif
 
 #if defined(__CUDACC__)
 #define SB_HD __host__ __device__ __forceinline__
@@ -66,7 +79,8 @@ enum Recipe : int {
     RC_AXPY,         // c0 * x0 + x1                 axpy!                             linalg.jl:23-31
     RC_AXPBY,        // c0 * x0 + c1 * x1            axpby!                            linalg.jl:32-42
     RC_ABS2,         // abs2(x0)                     C5  mapreduce(abs2, +, A; dims)
-    RC_COUNT_
+    RC_COUNT_,
+    RC_JIT = RC_COUNT_ // element function compiled at run time by NVRTC from the postfix program (csrc/jit.cu)
 };
 
 struct Program {
@@ -105,6 +119,7 @@ SB_HD void fast_divmod(const FastDiv &f, uint32_t x, uint32_t &q, uint32_t &r)
     q = (f.n == 1u) ? x : (sb_umulhi(x, f.mul) >> f.shr);
     r = x - q * f.n;
 }
+#if !defined(__CUDACC_RTC__)
 inline FastDiv make_fastdiv(uint32_t n)
 {
     FastDiv f{0u, 0u, n};
@@ -116,6 +131,7 @@ inline FastDiv make_fastdiv(uint32_t n)
     f.shr = p - 32u;
     return f;
 }
+#endif
 
 // ---- map plan (kernel parameter block) -------------------------------------------------------------
 struct MapParams {

@@ -6,7 +6,9 @@
 // and order signed zeros.
 #pragma once
 #include "common.hpp"
+#if !defined(__CUDACC_RTC__)
 #include <math.h>
+#endif
 
 namespace sb {
 
@@ -251,6 +253,15 @@ template <class CT, bool UNIFORM> SB_HD void store_elem(unsigned char *p, int dt
     }
 }
 
+SB_HD double sb_inf()
+{
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double(0x7ff0000000000000LL);
+#else
+    return (double)INFINITY;
+#endif
+}
+
 // ---- reduction operator / initop ----------------------------------------------------------------------
 template <class T> SB_HD T red_apply(int op, T a, T b)
 {
@@ -269,8 +280,8 @@ template <class T> SB_HD T red_neutral(int op)
     switch (op) {
     case OP_ADD: return make<T>(0.0, 0.0);
     case OP_MUL: return make<T>(1.0, 0.0);
-    case OP_MIN: return make<T>((double)INFINITY, 0.0);
-    default: return make<T>(-(double)INFINITY, 0.0);
+    case OP_MIN: return make<T>(sb_inf(), 0.0);
+    default: return make<T>(-sb_inf(), 0.0);
     }
 }
 template <class T> SB_HD T init_apply(int initop, double bre, double bim, T x)

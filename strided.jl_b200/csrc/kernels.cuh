@@ -1,87 +1,25 @@
 // kernels.cuh -- __global__ wrappers (sm_100a) around the tile bodies + the launch registry.
 #pragma once
-#include "map_tile.hpp"
-#include "reduce_tile.hpp"
+#include "kernel_bodies.cuh"
 #include "planner.hpp"
 #include <cuda_runtime.h>
 
 namespace sb {
 
-// ---- map ------------------------------------------------------------------------------------------------
-// Persistent CTAs: grid = min(ntiles, SMs x resident CTAs); each CTA walks tiles pos = blockIdx.x + i*grid,
-// so neighbouring CTAs work on neighbouring tiles at the same time (DRAM page / L2 locality, and aliased
-// operands such as A and A' meet in L2).
-// resident CTAs per SM the register allocator is asked to allow (value registers = NIN*EPT words of CT)
-template <class CT, int NIN, int EPT> struct MinBlocks {
-    static constexpr int words = NIN * EPT * (int)(sizeof(CT) / 4);
-    static constexpr int value = words <= 32 ? 4 : (words <= 64 ? 2 : 1);
-};
-
+// ---- statically instantiated kernels (the bodies live in kernel_bodies.cuh) ------------------------------------
 template <class CT, int RC, int NIN, int EPT, bool UNIFORM>
 __global__ void __launch_bounds__(THREADS, MinBlocks<CT, NIN, EPT>::value) map_tile_kernel(const __grid_constant__ MapParams P)
 {
-    extern __shared__ __align__(16) unsigned char sb_smem_raw[];
-    const int t = threadIdx.x;
-    MapThread<NIN + 1> th;
-    map_thread_init<NIN + 1>(P, t, th);
-    const bool staged = P.nstaged > 0;
-    const uint32_t ntiles = (uint32_t)P.ntiles;
-    for (uint32_t pos = blockIdx.x; pos < ntiles; pos += gridDim.x) {
-        MapTile<NIN + 1> tl;
-        map_tile_init<NIN + 1>(P, th, pos, tl);
-        CT v[NIN][EPT];
-        map_phase1<CT, NIN, EPT, UNIFORM>(P, th, tl, t, v, sb_smem_raw);
-        if (staged) __syncthreads();
-        map_phase2<CT, RC, NIN, EPT, UNIFORM>(P, th, tl, t, v, sb_smem_raw);
-        if (staged) __syncthreads();
-    }
+    map_tile_body<CT, RC, NIN, EPT, UNIFORM>(P);
 }
-
-// ---- reduce ---------------------------------------------------------------------------------------------
-template <class T> __device__ __forceinline__ T shfl_xor_any(T v, int mask)
-{
-    constexpr int W = sizeof(T) / 4;
-    union {
-        T v;
-        uint32_t w[W];
-    } a, b;
-    a.v = v;
-#pragma unroll
-    for (int i = 0; i < W; ++i) b.w[i] = __shfl_xor_sync(0xffffffffu, a.w[i], mask);
-    return b.v;
-}
-
 template <class AT, int RC, int NIN, int EPT, bool UNIFORM>
 __global__ void __launch_bounds__(THREADS, MinBlocks<AT, NIN, EPT>::value) reduce_tile_kernel(const __grid_constant__ ReduceParams P)
 {
-    extern __shared__ __align__(16) unsigned char sb_smem_raw[];
-    AT *smem = reinterpret_cast<AT *>(sb_smem_raw);
-    const int t = threadIdx.x;
-    const uint32_t bid = blockIdx.x;
-    red_accumulate<AT, RC, NIN, EPT, UNIFORM>(P, bid, t, smem);
-    __syncthreads();
-    if (P.warp_per_output) {
-        const int warp = t >> 5, lane = t & 31;
-        for (int o = warp; o < P.nout_tile; o += THREADS / 32) {
-            AT p = red_lane_partial<AT>(P, smem, o, lane);
-#pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) p = red_apply<AT>(P.op, p, shfl_xor_any(p, m));
-            if (lane == 0) red_finish<AT, UNIFORM>(P, bid, o, p);
-        }
-    } else {
-        for (int o = t; o < P.nout_tile; o += THREADS) red_finish<AT, UNIFORM>(P, bid, o, red_thread_partial<AT>(P, smem, o));
-    }
+    reduce_tile_body<AT, RC, NIN, EPT, UNIFORM>(P);
 }
-
 template <class AT, bool UNIFORM> __global__ void __launch_bounds__(THREADS) reduce_finalize_kernel(const __grid_constant__ ReduceParams P)
 {
-    const int64_t out_idx = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (out_idx >= P.nouttiles * (int64_t)P.nout_tile) return; // warp-uniform
-    AT p = red_finalize_lane<AT>(P, out_idx, lane);
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) p = red_apply<AT>(P.op, p, shfl_xor_any(p, m));
-    if (lane == 0) red_finalize_store<AT, UNIFORM>(P, out_idx, p);
+    reduce_finalize_body<AT, UNIFORM>(P);
 }
 
 // ---- registry ---------------------------------------------------------------------------------------------

@@ -879,6 +879,17 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
         tb[0] += ebits - used;
         used = ebits;
     }
+    if (const char *e = std::getenv("SB_TILE_BITS")) { // tuning knob: "b0,b1,..." log2 tile extents per canonical dim
+        int v[MAXD] = {0}, cnt = 0, sum = 0;
+        for (const char *q = e; *q && cnt < MAXD;) {
+            v[cnt++] = std::atoi(q);
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+        for (int i = 0; i < cnt; ++i) sum += v[i];
+        if (cnt == n && sum == ebits)
+            for (int i = 0; i < n; ++i) tb[i] = v[i];
+    }
     if (ntile_dims() > MAXTD) { err = "too many tile dims"; return SB_E_UNSUPPORTED; }
 
     // tile-dim slots in canonical (output) order
