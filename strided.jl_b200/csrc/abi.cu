@@ -460,19 +460,27 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
     } else {
         const ReduceEntry *k = find_reduce_kernel(plan.key);
         if (!k) return set_err(ctx, SB_E_UNSUPPORTED, "no reduce kernel instantiated for this plan");
-        if ((size_t)plan.scratch_bytes > ctx->scratch_bytes) {
+        // fixed-size counter region in front of the partials (a split plan has fewer output tiles than resident CTAs),
+        // so that partials of one plan can never alias the counters of another
+        const size_t counters_bytes = 64 * 1024;
+        if (plan.red.nsplit > 1 && (size_t)plan.red.nouttiles * 4 > counters_bytes) return set_err(ctx, SB_E_UNSUPPORTED, "too many output tiles for a split reduction");
+        const size_t scratch_need = plan.red.nsplit > 1 ? counters_bytes + (size_t)plan.scratch_bytes : 0;
+        if (scratch_need > ctx->scratch_bytes) {
             if (ctx->scratch) {
                 cudaStreamSynchronize(ctx->stream);
                 cudaFree(ctx->scratch);
                 ctx->scratch = nullptr;
                 ctx->scratch_bytes = 0;
             }
-            size_t want = std::max<size_t>((size_t)plan.scratch_bytes, 1 << 20);
+            size_t want = std::max<size_t>(scratch_need, 1 << 20);
             cudaError_t e = cudaMalloc(&ctx->scratch, want);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(scratch)");
+            e = cudaMemsetAsync(ctx->scratch, 0, want, ctx->stream); // arrival counters start at zero; kernels re-arm them
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMemset(scratch)");
             ctx->scratch_bytes = want;
         }
-        plan.red.scratch = (unsigned char *)ctx->scratch;
+        plan.red.counters = (uint32_t *)ctx->scratch;
+        plan.red.scratch = (unsigned char *)ctx->scratch + counters_bytes;
         cudaError_t e;
         if (jk) {
             void *args[] = {(void *)&plan.red};
@@ -483,7 +491,7 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
         if (e != cudaSuccess) return cuda_fail(ctx, e, "reduce_tile launch");
         ctx->stats.launches++;
         if (jk) ctx->stats.jit_launches++;
-        if (plan.finalize_threads > 0) {
+        if (false && plan.finalize_threads > 0) { // finalize is fused into reduce_tile (last-arriving CTA per output tile)
             const int64_t g = (plan.finalize_threads + (THREADS / 32) - 1) / (THREADS / 32); // one warp per output
             e = k->finalize(plan.red, (int)g, ctx->stream);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "reduce_finalize launch");

@@ -248,6 +248,7 @@ struct ReduceParams {
     int32_t warp_per_output;     // 1: layout [o][r], warp folds one output; 0: layout [r][o], thread per output
     OrderTab kept_order;         // decode of output number o -> kept tile coords (output order)
     unsigned char *scratch;      // partials [nsplit][nouttiles][nout_tile] of the ACCUMULATOR type
+    uint32_t *counters;          // one arrival counter per output tile: the LAST split CTA to arrive folds the partials
     int32_t ept;
     int32_t uniform;
     int32_t op;

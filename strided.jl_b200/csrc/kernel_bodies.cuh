@@ -68,6 +68,29 @@ template <class AT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forcein
     } else {
         for (int o = t; o < P.nout_tile; o += THREADS) red_finish<AT, UNIFORM>(P, bid, o, red_thread_partial<AT>(P, smem, o));
     }
+    if (P.nsplit > 1) {
+        // Fused finalize: the last split-CTA of an output tile to arrive folds that tile's partials in a fixed order
+        // (deterministic, no floating-point atomics) and applies op(initop(out), .) -- saves a second launch.
+        __shared__ unsigned int sb_is_last;
+        __threadfence(); // this CTA's partials are visible device-wide before it counts itself in
+        __syncthreads();
+        uint32_t split, out_tile;
+        fast_divmod(P.outdiv, bid, split, out_tile);
+        if (t == 0) sb_is_last = (atomicAdd(P.counters + out_tile, 1u) == (unsigned)P.nsplit - 1u) ? 1u : 0u;
+        __syncthreads();
+        if (sb_is_last) {
+            __threadfence();
+            const int warp = t >> 5, lane = t & 31;
+            for (int o = warp; o < P.nout_tile; o += THREADS / 32) {
+                const int64_t out_idx = (int64_t)out_tile * P.nout_tile + o;
+                AT p = red_finalize_lane<AT>(P, out_idx, lane);
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) p = red_apply<AT>(P.op, p, shfl_xor_any(p, m));
+                if (lane == 0) red_finalize_store<AT, UNIFORM>(P, out_idx, p);
+            }
+            if (t == 0) P.counters[out_tile] = 0u; // re-arm for the next launch
+        }
+    }
 }
 
 template <class AT, bool UNIFORM> __device__ __forceinline__ void reduce_finalize_body(const ReduceParams &P)

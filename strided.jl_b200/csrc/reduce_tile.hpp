@@ -206,7 +206,23 @@ template <class AT, bool UNIFORM> SB_HD void red_finish(const ReduceParams &P, u
     store_elem<AT, UNIFORM>(P.base[0] + off, P.dtype[0], P.conj[0], red_apply<AT>(P.op, x, p));
 }
 
-// finalize kernel: one WARP per output (out_tile, o).  Lane l folds partials of splits l, l+32, ... in split
+// partials are written by other SMs in the same launch: read them through L2 (ld.global.cg), never a stale L1 line
+template <class AT> SB_HD AT load_partial(const AT *p)
+{
+#if defined(__CUDA_ARCH__)
+    AT v;
+    constexpr int W = sizeof(AT) / 4;
+    const unsigned int *src = reinterpret_cast<const unsigned int *>(p);
+    unsigned int *dst = reinterpret_cast<unsigned int *>(&v);
+#pragma unroll
+    for (int i = 0; i < W; ++i) dst[i] = __ldcg(src + i);
+    return v;
+#else
+    return *p;
+#endif
+}
+
+// finalize: one WARP per output (out_tile, o).  Lane l folds partials of splits l, l+32, ... in split
 // order; the 32 lane results are then combined by a shuffle butterfly (fixed order -> deterministic).
 template <class AT> SB_HD AT red_finalize_lane(const ReduceParams &P, int64_t out_idx, int lane)
 {
@@ -216,7 +232,7 @@ template <class AT> SB_HD AT red_finalize_lane(const ReduceParams &P, int64_t ou
     for (int s = lane; s < P.nsplit; s += 128) { // four independent loads in flight, folded in split order
         AT v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = (s + 32 * u < P.nsplit) ? sc[(int64_t)(s + 32 * u) * stride + out_idx] : red_neutral<AT>(P.op);
+        for (int u = 0; u < 4; ++u) v[u] = (s + 32 * u < P.nsplit) ? load_partial(sc + (int64_t)(s + 32 * u) * stride + out_idx) : red_neutral<AT>(P.op);
 #pragma unroll
         for (int u = 0; u < 4; ++u) p = red_apply<AT>(P.op, p, v[u]);
     }

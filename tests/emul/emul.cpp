@@ -131,6 +131,7 @@ template <class AT, int RC, int NIN, int EPT, bool U> static void run_reduce(con
                 for (int o = t; o < P.nout_tile; o += THREADS) red_finish<AT, U>(P, bid, o, red_thread_partial<AT>(P, smem.data(), o));
         }
     }
+    // the fused finalize: emulated after all CTAs (on the GPU the last-arriving CTA of each output tile does it)
     if (plan.finalize_threads > 0) {
         for (int64_t out_idx = 0; out_idx < plan.finalize_threads; ++out_idx) {
             AT p[32];
