@@ -1136,7 +1136,9 @@ int plan_reduce(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &
     // splits of the reduced index space
     const int64_t target = (int64_t)dev.sm_count * dev.ctas_per_sm;
     int64_t nsplit = 1;
-    if (P.nouttiles < target) nsplit = std::min<int64_t>(P.nrsteps, (target + P.nouttiles - 1) / P.nouttiles);
+    // at least 4 tile steps (>= 32 KB of input) per split: tiny reductions are latency-bound, more partials only
+    // lengthen the final fold
+    if (P.nouttiles < target) nsplit = std::min<int64_t>(std::max<int64_t>(1, P.nrsteps / 4), (target + P.nouttiles - 1) / P.nouttiles);
     P.steps_per_split = (P.nrsteps + nsplit - 1) / nsplit;
     nsplit = (P.nrsteps + P.steps_per_split - 1) / P.steps_per_split;
     if (nsplit > 0x7fffffff) { err = "too many splits"; return SB_E_UNSUPPORTED; }

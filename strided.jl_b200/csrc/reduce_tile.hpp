@@ -229,12 +229,12 @@ template <class AT> SB_HD AT red_finalize_lane(const ReduceParams &P, int64_t ou
     const AT *sc = reinterpret_cast<const AT *>(P.scratch);
     const int64_t stride = P.nouttiles * (int64_t)P.nout_tile;
     AT p = red_neutral<AT>(P.op);
-    for (int s = lane; s < P.nsplit; s += 128) { // four independent loads in flight, folded in split order
-        AT v[4];
+    for (int s = lane; s < P.nsplit; s += 256) { // eight independent loads in flight, folded in split order
+        AT v[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = (s + 32 * u < P.nsplit) ? load_partial(sc + (int64_t)(s + 32 * u) * stride + out_idx) : red_neutral<AT>(P.op);
+        for (int u = 0; u < 8; ++u) v[u] = (s + 32 * u < P.nsplit) ? load_partial(sc + (int64_t)(s + 32 * u) * stride + out_idx) : red_neutral<AT>(P.op);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) p = red_apply<AT>(P.op, p, v[u]);
+        for (int u = 0; u < 8; ++u) p = red_apply<AT>(P.op, p, v[u]);
     }
     return p;
 }
