@@ -491,12 +491,7 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
         if (e != cudaSuccess) return cuda_fail(ctx, e, "reduce_tile launch");
         ctx->stats.launches++;
         if (jk) ctx->stats.jit_launches++;
-        if (false && plan.finalize_threads > 0) { // finalize is fused into reduce_tile (last-arriving CTA per output tile)
-            const int64_t g = (plan.finalize_threads + (THREADS / 32) - 1) / (THREADS / 32); // one warp per output
-            e = k->finalize(plan.red, (int)g, ctx->stream);
-            if (e != cudaSuccess) return cuda_fail(ctx, e, "reduce_finalize launch");
-            ctx->stats.launches++;
-        }
+        // (the fold of the split partials is fused into reduce_tile: last-arriving CTA per output tile)
     }
     return SB_OK;
 }
