@@ -107,6 +107,7 @@ static bool encode_tma_maps(const Plan &plan, CUtensorMap *maps)
 struct CachedPlan {
     Plan plan;
     void *dev_order = nullptr;
+    void *dev_desc = nullptr;
 };
 
 struct sb_ctx {
@@ -134,6 +135,8 @@ static void clear_plans(sb_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->plans)
         if (kv.second.dev_order) cudaFree(kv.second.dev_order);
+    for (auto &kv : ctx->plans)
+        if (kv.second.dev_desc) cudaFree(kv.second.dev_desc);
     ctx->plans.clear();
 }
 
@@ -379,12 +382,23 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
             cp.plan.tile_order.clear();
             cp.plan.tile_order.shrink_to_fit();
         }
+        if (!cp.plan.tile_desc.empty()) { // per-tile records of the TMA path
+            cudaSetDevice(ctx->device);
+            const size_t bytes = cp.plan.tile_desc.size() * sizeof(TileDesc);
+            cudaError_t e = cudaMalloc(&cp.dev_desc, bytes);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(cp.dev_desc, cp.plan.tile_desc.data(), bytes, cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "tile descriptor upload");
+            cp.plan.tile_desc.clear();
+            cp.plan.tile_desc.shrink_to_fit();
+        }
         hit = ctx->plans.emplace(std::move(key), std::move(cp)).first;
     } else {
         ctx->stats.plans_cached++;
     }
     Plan plan = hit->second.plan; // copy: bases are bound per call
     plan.map.tile_order = (const int32_t *)hit->second.dev_order;
+    plan.map.tile_desc = (const TileDesc *)hit->second.dev_desc;
     for (int k = 0; k < MAXO; ++k) {
         plan.map.base[k] = (unsigned char *)desc.base[plan.base_src[k] < desc.nops ? plan.base_src[k] : 0];
         plan.red.base[k] = plan.map.base[k];

@@ -133,6 +133,16 @@ inline FastDiv make_fastdiv(uint32_t n)
 }
 #endif
 
+// ---- per-tile descriptor table (TMA path) ----------------------------------------------------------------
+// The no-load/no-store diagnostic (profiles/r01_v8_*) showed the TMA kernel bound by its own per-tile instruction
+// overhead (~270 warp-instructions per tile, of which ~80 touch data).  Everything that depends only on the tile is
+// therefore precomputed on the host, in LAUNCH order: one 32-byte record per tile, read with a single uniform load.
+struct TileDesc {
+    int32_t origin[5];  // element origin per canonical dim (TMA coordinates are a permutation of these)
+    uint32_t id_full;   // bit 31: interior tile (no masking); bits 0..30: tile id (edge masks)
+    int64_t out_off;    // byte offset of the tile origin in the output
+};
+
 // ---- map plan (kernel parameter block) -------------------------------------------------------------
 struct MapParams {
     int32_t ndim;  // canonical dims (size-1 dropped, fused, sorted by |output stride|)
@@ -148,6 +158,7 @@ struct MapParams {
     uint8_t tdim[MAXTD];  // tile-dim slot -> canonical dim
     int64_t ntiles;
     const int32_t *tile_order; // optional device table: launch position -> tile id (alias-aware order)
+    const TileDesc *tile_desc; // optional device table (TMA path): launch position -> precomputed tile record
     unsigned char *base[MAXO];
     int64_t strides[MAXO][MAXD]; // elements
     uint8_t dtype[MAXO];

@@ -738,8 +738,11 @@ bool plan_tma(const Canon &c, const MapParams &P, const int *tdim, Plan &plan)
     for (int k = 0; k < nin; ++k) nboxes += T.op[k].nbox;
     if (nboxes > 32) return false; // one producer lane per box
     T.stage_bytes = off;
-    int ns = (int)(98304 / std::max(1, off));
-    if (ns < 2) return false;
+    // 2 stages of <= 32 KB leave room for 3 resident CTAs per SM (27 warps), measured best for the 2-input case
+    // (profiles/r01_v8_tile_desc_table.txt); single-input transposes (16 KB stages) get 4 stages
+    int ns = (int)(65536 / std::max(1, off));
+    if (off > 110 * 1024) return false;
+    if (ns < 2) ns = 2;
     if (ns > 4) ns = 4;
     if (const char *e = std::getenv("SB_TMA_STAGES")) {
         const int v = std::atoi(e);
@@ -956,6 +959,10 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
     const int V = (uniform && esz < 16 && want_vec) ? 16 / esz : 1;
     const int vbits = (V > 1 && ept % V == 0) ? ilog2_ceil(V) : 0;
     P.vbits = vbits;
+    if (const char *dbg = std::getenv("SB_DEBUG")) { // diagnostics only (tools/): results are WRONG with these
+        if (std::strstr(dbg, "nostore")) P.uniform |= 0x100;
+        if (std::strstr(dbg, "noload")) P.uniform |= 0x200;
+    }
     auto aligned16 = [&](int k) {
         if (((uintptr_t)c.base[k] & 15u) != 0) return false;
         for (int i = 0; i < n; ++i)
@@ -1004,7 +1011,25 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
     if (plan.smem_bytes > 200 * 1024) { err = "staging buffers exceed shared memory"; return SB_E_UNSUPPORTED; }
     plan.grid = std::min<int64_t>(P.ntiles, (int64_t)dev.sm_count * dev.ctas_per_sm);
     if (build_tile_order(c, P, plan.tile_order)) plan.note = "alias-aware tile order";
-    plan_tma(c, P, tdim, plan);
+    if (plan_tma(c, P, tdim, plan) && P.ntiles <= (1 << 20) && !std::getenv("SB_NO_TILE_DESC")) {
+        plan.tile_desc.resize((size_t)P.ntiles);
+        for (int64_t pos = 0; pos < P.ntiles; ++pos) {
+            uint32_t id = plan.tile_order.empty() ? (uint32_t)pos : (uint32_t)plan.tile_order[(size_t)pos];
+            TileDesc &td = plan.tile_desc[(size_t)pos];
+            td.id_full = id;
+            td.out_off = 0;
+            bool full = true;
+            for (int d = 0; d < 5; ++d) td.origin[d] = 0;
+            for (int d = 0; d < n; ++d) {
+                const uint32_t cd = id % (uint32_t)P.ntile[d];
+                id /= (uint32_t)P.ntile[d];
+                td.origin[d] = (int32_t)cd * P.tile_b[d];
+                td.out_off += (int64_t)cd * P.tstep[0][d];
+                full = full && ((int32_t)cd < P.nfull[d]);
+            }
+            if (full) td.id_full |= 0x80000000u;
+        }
+    }
     plan.elements = 1;
     for (int i = 0; i < n; ++i) plan.elements *= c.dims[i];
     return SB_OK;

@@ -51,6 +51,7 @@ struct Plan {
         uint32_t box[TMA_MAXRANK] = {0};
     } tma_global[TMA_MAXIN];
     int64_t tma_smem_bytes = 0;
+    std::vector<TileDesc> tile_desc; // per-tile records in launch order (uploaded with the plan)
     std::string note;
 };
 

@@ -155,6 +155,14 @@ map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaP
         }
         const CUtensorMap *map = bk == 0 ? &m0 : bk == 1 ? &m1 : bk == 2 ? &m2 : &m3;
         const uint32_t box_dst = bk >= 0 ? (uint32_t)T.op[bk].smem_off + (uint32_t)(bq * T.op[bk].box_bytes) : 0u;
+        int my_cdim[TMA_MAXRANK] = {0, 0, 0, 0, 0};
+        int my_rank = 1, my_inner_step = 0;
+        if (bk >= 0) {
+#pragma unroll
+            for (int i = 0; i < TMA_MAXRANK; ++i) my_cdim[i] = (i < T.op[bk].rank) ? (int)T.op[bk].cdim[i] : 0;
+            my_rank = T.op[bk].rank;
+            my_inner_step = T.op[bk].inner_step;
+        }
         int stage = 0;
         uint32_t parity = 1; // a fresh barrier passes a wait on parity 1: every stage starts out empty
         for (uint32_t pos = blockIdx.x; pos < ntiles; pos += grid) {
@@ -162,9 +170,30 @@ map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaP
             const uint32_t fb = smem_u32(&full_bar[stage]);
             if (lane == 0) mbar_expect_tx(fb, (uint32_t)T.stage_bytes);
             __syncwarp();
-            if (bk >= 0) {
-                const uint32_t id = P.tile_order ? (uint32_t)P.tile_order[pos] : pos;
-                tma_issue_box(P, T.op[bk], map, bq, id, ring_u32 + (uint32_t)(stage * T.stage_bytes) + box_dst, fb);
+            if (P.uniform & 0x200) { // diagnostic (SB_DEBUG=noload): complete the barrier without moving data
+                if (lane == 0) asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(fb), "r"((uint32_t)T.stage_bytes) : "memory");
+            } else if (bk >= 0) {
+                const uint32_t dst = ring_u32 + (uint32_t)(stage * T.stage_bytes) + box_dst;
+                if (P.tile_desc) { // precomputed tile record: coordinates are a per-lane permutation of the origins
+                    const TileDesc td = P.tile_desc[pos];
+                    int32_t crd[TMA_MAXRANK];
+#pragma unroll
+                    for (int i = 0; i < TMA_MAXRANK; ++i) {
+                        const int cd = my_cdim[i];
+                        crd[i] = cd == 0 ? td.origin[0] : cd == 1 ? td.origin[1] : cd == 2 ? td.origin[2] : cd == 3 ? td.origin[3] : td.origin[4];
+                    }
+                    crd[0] += bq * my_inner_step;
+                    switch (my_rank) {
+                    case 1: tma_load<1>(dst, map, fb, crd); break;
+                    case 2: tma_load<2>(dst, map, fb, crd); break;
+                    case 3: tma_load<3>(dst, map, fb, crd); break;
+                    case 4: tma_load<4>(dst, map, fb, crd); break;
+                    default: tma_load<5>(dst, map, fb, crd); break;
+                    }
+                } else {
+                    const uint32_t id = P.tile_order ? (uint32_t)P.tile_order[pos] : pos;
+                    tma_issue_box(P, T.op[bk], map, bq, id, dst, fb);
+                }
             }
             if (++stage == S) {
                 stage = 0;
@@ -182,7 +211,14 @@ map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaP
         uint32_t parity = 0;
         for (uint32_t pos = blockIdx.x; pos < ntiles; pos += grid) {
             MapTile<1> tl;
-            map_tile_init<1>(P, th0, pos, tl);
+            if (P.tile_desc) {
+                const TileDesc td = P.tile_desc[pos];
+                tl.id = td.id_full & 0x7fffffffu;
+                tl.full = (td.id_full >> 31) != 0;
+                tl.ptr[0] = P.base[0] + (td.out_off + th0.g_toff[0]);
+            } else {
+                map_tile_init<1>(P, th0, pos, tl);
+            }
             mbar_wait(smem_u32(&full_bar[stage]), parity);
             tma_consume<CT, RC, NIN, EPT>(P, T, th, th0, tl, t, ring + (size_t)stage * T.stage_bytes);
             __syncwarp();

@@ -66,7 +66,16 @@ SB_HD void tma_consume(const MapParams &P, const TmaParams &T, const TmaThread<N
     }
     ElemFn<CT, RC> fn;
     unsigned char *ob = const_cast<unsigned char *>(tl.ptr[0]);
-    if (tl.full && VEC && P.gvec[0]) {
+    if (P.uniform & 0x100) { // diagnostic (SB_DEBUG=nostore): keep the loads and the math, drop the stores
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            CT a[NIN];
+#pragma unroll
+            for (int k = 0; k < NIN; ++k) a[k] = v[k][j];
+            const CT r = fn.template eval<NIN>(P.prog, a);
+            if (re_of(r) == (typename traits<CT>::real)1.2345678e-300f) store_elem<CT, true>(ob + P.g_joff[0][j], P.dtype[0], 0, r);
+        }
+    } else if (tl.full && VEC && P.gvec[0]) {
 #pragma unroll
         for (int j = 0; j < EPT; j += V) {
             typename VecOf<CT>::type x;
