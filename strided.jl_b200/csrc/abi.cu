@@ -2,7 +2,7 @@
 //
 // There is NO CPU execution path here: without a CUDA device every compute entry point returns
 // SB_E_NODEVICE.  (sb_plan_describe is pure host planning and works anywhere.)
-#include "tma_kernel.cuh"
+#include "orbit_kernel.cuh"
 #include "jit.hpp"
 
 #include <cstdio>
@@ -104,10 +104,36 @@ static bool encode_tma_maps(const Plan &plan, CUtensorMap *maps)
     return true;
 }
 
+// parent (load) and output (store) maps of the alias-fused orbit kernel: dense boxes, no swizzle
+static bool encode_orbit_maps(const Plan &plan, CUtensorMap *maps)
+{
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return false;
+    for (int w = 0; w < 2; ++w) {
+        const Plan::TmaGlobal &g = plan.orbit_global[w];
+        void *base = plan.map.base[w == 0 ? 1 : 0];
+        if (((uintptr_t)base & 15u) != 0) return false;
+        cuuint64_t gdim[TMA_MAXRANK], gstr[TMA_MAXRANK];
+        cuuint32_t box[TMA_MAXRANK], estr[TMA_MAXRANK];
+        for (int i = 0; i < g.rank; ++i) {
+            gdim[i] = g.gdim[i];
+            box[i] = g.box[i];
+            estr[i] = 1;
+            if (i > 0) gstr[i - 1] = g.gstride_bytes[i];
+        }
+        const CUtensorMapDataType dt = g.elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+        const CUresult r = enc(&maps[w], dt, (cuuint32_t)g.rank, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return false;
+    }
+    return true;
+}
+
 struct CachedPlan {
     Plan plan;
     void *dev_order = nullptr;
     void *dev_desc = nullptr;
+    void *dev_orbit = nullptr;
 };
 
 struct sb_ctx {
@@ -137,6 +163,8 @@ static void clear_plans(sb_ctx *ctx)
         if (kv.second.dev_order) cudaFree(kv.second.dev_order);
     for (auto &kv : ctx->plans)
         if (kv.second.dev_desc) cudaFree(kv.second.dev_desc);
+    for (auto &kv : ctx->plans)
+        if (kv.second.dev_orbit) cudaFree(kv.second.dev_orbit);
     ctx->plans.clear();
 }
 
@@ -302,6 +330,8 @@ int sb_plan_describe(sb_ctx *ctx, const sb_desc *desc, char *buf, size_t buflen)
 
 } // extern "C"
 
+static void operand_range(const sb_desc &d, int k, int64_t &lo, int64_t &hi);
+
 // ---- launch -----------------------------------------------------------------------------------------------
 static int occupancy_of(sb_ctx *ctx, const void *func, cudaError_t (*occ)(int *, size_t), size_t smem, int &nb)
 {
@@ -392,6 +422,16 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
             cp.plan.tile_desc.clear();
             cp.plan.tile_desc.shrink_to_fit();
         }
+        if (!cp.plan.orbit_items.empty()) { // work items of the alias-fused orbit kernel
+            cudaSetDevice(ctx->device);
+            const size_t bytes = cp.plan.orbit_items.size() * sizeof(OrbitItem);
+            cudaError_t e = cudaMalloc(&cp.dev_orbit, bytes);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(cp.dev_orbit, cp.plan.orbit_items.data(), bytes, cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "orbit item upload");
+            cp.plan.orbit_items.clear();
+            cp.plan.orbit_items.shrink_to_fit();
+        }
         hit = ctx->plans.emplace(std::move(key), std::move(cp)).first;
     } else {
         ctx->stats.plans_cached++;
@@ -399,6 +439,7 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
     Plan plan = hit->second.plan; // copy: bases are bound per call
     plan.map.tile_order = (const int32_t *)hit->second.dev_order;
     plan.map.tile_desc = (const TileDesc *)hit->second.dev_desc;
+    plan.orbit.items = (const OrbitItem *)hit->second.dev_orbit;
     for (int k = 0; k < MAXO; ++k) {
         plan.map.base[k] = (unsigned char *)desc.base[plan.base_src[k] < desc.nops ? plan.base_src[k] : 0];
         plan.red.base[k] = plan.map.base[k];
@@ -442,6 +483,27 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
             if (e != cudaSuccess) return cuda_fail(ctx, e, "jit map launch");
             ctx->stats.launches++;
             ctx->stats.jit_launches++;
+            return SB_OK;
+        }
+    }
+    if (plan.kind == PLAN_MAP && plan.orbit_ok && plan.orbit.items) { // alias-fused orbits: parent read once, output written once
+        // bind-time conditions: the output must not overlap the parent (blocks are re-read after other tiles were stored)
+        int64_t lo0, hi0, lo1, hi1;
+        operand_range(desc, plan.base_src[0], lo0, hi0);
+        operand_range(desc, plan.base_src[1], lo1, hi1);
+        const uintptr_t o0 = (uintptr_t)plan.map.base[0], p0 = (uintptr_t)plan.map.base[1];
+        const bool overlap = (o0 + (uintptr_t)lo0 < p0 + (uintptr_t)hi1) && (p0 + (uintptr_t)lo1 < o0 + (uintptr_t)hi0);
+        const OrbitEntry *ok = overlap ? nullptr : find_orbit_kernel(KernelKey{plan.key.ct, plan.key.recipe, plan.orbit.nin, plan.orbit.ept, 1});
+        alignas(64) CUtensorMap maps[2];
+        if (ok && encode_orbit_maps(plan, maps)) {
+            int nb = 1;
+            rc = occupancy_of(ctx, ok->func, ok->occupancy, (size_t)plan.orbit_smem_bytes, nb);
+            if (rc != SB_OK) return rc;
+            int64_t grid = std::min<int64_t>(plan.orbit.nitems, (int64_t)ctx->dev.sm_count * nb);
+            if (grid < 1) grid = 1;
+            cudaError_t e = ok->launch(plan.orbit, maps, (int)grid, (size_t)plan.orbit_smem_bytes, ctx->stream);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "map_orbit launch");
+            ctx->stats.launches++;
             return SB_OK;
         }
     }

@@ -224,6 +224,43 @@ struct TmaParams {
 };
 SB_HD uint32_t swizzle128(uint32_t d) { return d ^ (((d >> 7) & 7u) << 4); }
 
+// ---- alias-fused ("orbit") map plan --------------------------------------------------------------------------
+// When every input is a dim-permuted view of ONE parent (A and A' in `(A .+ A') ./ 2`; the four rotations of the
+// 4-way permutedims sum, README.md:91-104), the output tiles fall into orbits under the group generated by the
+// permutations, and the tiles of one orbit need exactly the parent blocks of that orbit.  A work item is one
+// orbit: its <= ORB_MAXG parent blocks are fetched ONCE by TMA (cp.async.bulk.tensor, dense box), every output
+// tile of the orbit is computed from shared memory (each view reads "its" block through a permuted address
+// functional), staged in output layout and written back with a TMA store.  SM<->L2 traffic drops from
+// (nin + 1) x to 2 x the array; the reference gets the same effect from cache blocking inside one task
+// (src/mapreduce.jl:463-500).
+//
+// Thread t handles elements u = t + 256*j of a tile THROUGH A GF(2)-LINEAR MAP x = M u onto the tile's bit-field
+// coordinates, chosen by the planner so that all views' shared-memory reads and the staging write of a warp are
+// bank-conflict free.  Every address functional is again  T(t) XOR J[j].
+constexpr int ORB_MAXG = 4;      // tiles (= parent blocks) per work item
+constexpr int ORB_MAXIN = 4;
+constexpr int ORB_THREADS = THREADS + 32; // 8 consumer warps + 1 producer warp
+struct OrbitItem {
+    int32_t ntile;
+    int32_t pad_;
+    int32_t pcrd[ORB_MAXG][TMA_MAXRANK]; // TMA coordinates (parent dim order) of parent block s
+    int32_t ocrd[ORB_MAXG][TMA_MAXRANK]; // TMA coordinates (output dim order) of output tile m
+    uint8_t slot[ORB_MAXG][ORB_MAXIN];   // input k of output tile m reads parent block slot[m][k]
+};
+struct OrbitParams {
+    int32_t nin, rank;
+    int32_t nstage;      // depth of the input ring (stages of gmax blocks)
+    int32_t tile_bytes;  // one parent block = one output tile
+    int32_t stage_bytes; // gmax * tile_bytes
+    int32_t gmax;
+    int32_t ept;
+    int32_t nitems;
+    const OrbitItem *items;
+    uint32_t tcol[ORB_MAXIN + 1][LOG_THREADS]; // byte-address image of thread bit i; view 0 = output staging, k = input k
+    uint32_t jtab[ORB_MAXIN + 1][MAXEPT];      // byte-address image of j
+    Program prog;
+};
+
 // ---- reduce plan ------------------------------------------------------------------------------------
 struct ReduceParams {
     int32_t ndim, nops, ntd;

@@ -1,0 +1,183 @@
+// orbit_kernel.cuh -- sm_100a kernel: alias-fused strided map (see common.hpp "orbit" and orbit_tile.hpp).
+//
+//   producer warp : per work item (orbit) waits for a free stage, arms its full barrier with ntile * tile_bytes and
+//                   lets lane s issue the cp.async.bulk.tensor of parent block s        (SASS: UTMALDG, SYNCS)
+//   consumer warps: wait on the full barrier; for each output tile of the orbit compute 256*EPT elements from shared
+//                   memory into one of two staging buffers (fence.proxy.async), meet on a named barrier, and thread 0
+//                   issues the TMA store of the tile (cp.async.bulk.tensor ... bulk_group; SASS: UTMASTG) -- it runs
+//                   while the next tile is computed into the other staging buffer; the stage is released per warp.
+// Out-of-bounds parts of edge blocks are zero-filled on load and clipped on store by the TMA unit: no masks anywhere.
+#pragma once
+#include "tma_kernel.cuh"
+#include "orbit_tile.hpp"
+
+namespace sb {
+
+template <int RANK> __device__ __forceinline__ void tma_store(const CUtensorMap *map, uint32_t src, const int32_t *c);
+template <> __device__ __forceinline__ void tma_store<1>(const CUtensorMap *map, uint32_t src, const int32_t *c)
+{
+    asm volatile("cp.async.bulk.tensor.1d.global.shared::cta.bulk_group [%0, {%2}], [%1];" ::"l"(map), "r"(src), "r"(c[0]) : "memory");
+}
+template <> __device__ __forceinline__ void tma_store<2>(const CUtensorMap *map, uint32_t src, const int32_t *c)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c[0]), "r"(c[1])
+                 : "memory");
+}
+template <> __device__ __forceinline__ void tma_store<3>(const CUtensorMap *map, uint32_t src, const int32_t *c)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c[0]),
+                 "r"(c[1]), "r"(c[2])
+                 : "memory");
+}
+template <> __device__ __forceinline__ void tma_store<4>(const CUtensorMap *map, uint32_t src, const int32_t *c)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src), "r"(c[0]),
+                 "r"(c[1]), "r"(c[2]), "r"(c[3])
+                 : "memory");
+}
+template <> __device__ __forceinline__ void tma_store<5>(const CUtensorMap *map, uint32_t src, const int32_t *c)
+{
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map), "r"(src),
+                 "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4])
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_rank(int rank, uint32_t dst, const CUtensorMap *map, uint32_t bar, const int32_t *c)
+{
+    switch (rank) {
+    case 1: tma_load<1>(dst, map, bar, c); break;
+    case 2: tma_load<2>(dst, map, bar, c); break;
+    case 3: tma_load<3>(dst, map, bar, c); break;
+    case 4: tma_load<4>(dst, map, bar, c); break;
+    default: tma_load<5>(dst, map, bar, c); break;
+    }
+}
+__device__ __forceinline__ void tma_store_rank(int rank, const CUtensorMap *map, uint32_t src, const int32_t *c)
+{
+    switch (rank) {
+    case 1: tma_store<1>(map, src, c); break;
+    case 2: tma_store<2>(map, src, c); break;
+    case 3: tma_store<3>(map, src, c); break;
+    case 4: tma_store<4>(map, src, c); break;
+    default: tma_store<5>(map, src, c); break;
+    }
+}
+
+constexpr int ORB_MAXSTAGE = 8;
+
+template <class CT, int RC, int NIN, int EPT>
+__global__ void __launch_bounds__(ORB_THREADS, 2)
+map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ CUtensorMap min, const __grid_constant__ CUtensorMap mout)
+{
+    extern __shared__ unsigned char sb_orbit_smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[ORB_MAXSTAGE];
+    __shared__ __align__(8) uint64_t empty_bar[ORB_MAXSTAGE];
+    // ring (nstage stages of gmax blocks) followed by two staging buffers; TMA needs 128-byte aligned boxes
+    unsigned char *ring = sb_orbit_smem_raw + ((0u - smem_u32(sb_orbit_smem_raw)) & 127u); // (offset form keeps the address space known: LDS/STS)
+    const uint32_t ring_u32 = smem_u32(ring);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = O.nstage;
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t nitems = (uint32_t)O.nitems;
+    const uint32_t grid = gridDim.x;
+    if (warp == THREADS / 32) {
+        // ---------------- producer warp ----------------
+        int stage = 0;
+        uint32_t parity = 1; // a fresh barrier passes a wait on parity 1: every stage starts out empty
+        for (uint32_t pos = blockIdx.x; pos < nitems; pos += grid) {
+            const OrbitItem *it = O.items + pos;
+            const int ntile = it->ntile;
+            int32_t crd[TMA_MAXRANK] = {0, 0, 0, 0, 0};
+            if (lane < ntile) {
+#pragma unroll
+                for (int i = 0; i < TMA_MAXRANK; ++i) crd[i] = it->pcrd[lane][i];
+            }
+            mbar_wait(smem_u32(&empty_bar[stage]), parity);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            if (lane == 0) mbar_expect_tx(fb, (uint32_t)(ntile * O.tile_bytes));
+            __syncwarp();
+            if (lane < ntile) tma_load_rank(O.rank, ring_u32 + (uint32_t)(stage * O.stage_bytes + lane * O.tile_bytes), &min, fb, crd);
+            if (++stage == S) {
+                stage = 0;
+                parity ^= 1u;
+            }
+        }
+    } else {
+        // ---------------- consumer warps ----------------
+        OrbitThread<NIN> th;
+        orbit_thread_init<NIN>(O, tid, th);
+        const uint32_t staging0 = (uint32_t)(S * O.stage_bytes);
+        int stage = 0;
+        uint32_t parity = 0, nout = 0;
+        for (uint32_t pos = blockIdx.x; pos < nitems; pos += grid) {
+            const OrbitItem *it = O.items + pos;
+            const int ntile = it->ntile;
+            mbar_wait(smem_u32(&full_bar[stage]), parity);
+            for (int m = 0; m < ntile; ++m) {
+                const uint32_t slots = *reinterpret_cast<const uint32_t *>(it->slot[m]);
+                const uint32_t sbuf_off = staging0 + (nout & 1u) * (uint32_t)O.tile_bytes;
+                orbit_compute<CT, RC, NIN, EPT>(O, th, ring, (uint32_t)(stage * O.stage_bytes), slots, sbuf_off);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the TMA store
+                // the store issued one tile ago read the OTHER staging buffer: it must be done before anyone writes there
+                if (tid == 0 && nout > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+                if (tid == 0) {
+                    int32_t crd[TMA_MAXRANK];
+#pragma unroll
+                    for (int i = 0; i < TMA_MAXRANK; ++i) crd[i] = it->ocrd[m][i];
+                    tma_store_rank(O.rank, &mout, ring_u32 + sbuf_off, crd);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                ++nout;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage])); // this warp is done with the stage
+            if (++stage == S) {
+                stage = 0;
+                parity ^= 1u;
+            }
+        }
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // stores complete before the CTA retires
+    }
+}
+
+struct OrbitEntry {
+    KernelKey key;
+    cudaError_t (*launch)(const OrbitParams &, const CUtensorMap *, int grid, size_t smem, cudaStream_t);
+    cudaError_t (*occupancy)(int *nblocks, size_t smem);
+    const void *func;
+};
+
+template <class CT, int RC, int NIN, int EPT> struct OrbitLaunch {
+    static cudaError_t launch(const OrbitParams &O, const CUtensorMap *maps, int grid, size_t smem, cudaStream_t s)
+    {
+        auto k = map_orbit_kernel<CT, RC, NIN, EPT>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k<<<grid, ORB_THREADS, smem, s>>>(O, maps[0], maps[1]);
+        return cudaGetLastError();
+    }
+    static cudaError_t occupancy(int *nb, size_t smem)
+    {
+        auto k = map_orbit_kernel<CT, RC, NIN, EPT>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, ORB_THREADS, smem);
+    }
+    static const void *func() { return (const void *)map_orbit_kernel<CT, RC, NIN, EPT>; }
+};
+
+#define SB_ORBIT_ENTRY(CT, DT, RC, NIN, EPT)                                                                         \
+    OrbitEntry { KernelKey{DT, RC, NIN, EPT, 1}, &OrbitLaunch<CT, RC, NIN, EPT>::launch, &OrbitLaunch<CT, RC, NIN, EPT>::occupancy, \
+                 OrbitLaunch<CT, RC, NIN, EPT>::func() }
+
+const OrbitEntry *orbit_table(int *n);
+const OrbitEntry *find_orbit_kernel(const KernelKey &k);
+
+} // namespace sb

@@ -756,6 +756,337 @@ bool plan_tma(const Canon &c, const MapParams &P, const int *tdim, Plan &plan)
     return true;
 }
 
+// ---- alias-fused ("orbit") variant ---------------------------------------------------------------------------
+// mirrored by csrc/kernels_orbit.cu
+bool orbit_instantiated(int ct, int recipe, int nin, int ept)
+{
+    if (ct != F32 && ct != F64) return false;
+    if (ept != 4 && ept != 8 && ept != 16) return false;
+    switch (recipe) {
+    case RC_ADD2: case RC_ADD2_MUL: case RC_ADD2_DIV: case RC_AXPY: case RC_AXPBY: return nin == 2;
+    case RC_SUM3: return nin == 3;
+    case RC_SUM4: return nin == 4;
+    default: return false;
+    }
+}
+
+int gf2_rank(const uint32_t *v, int n)
+{
+    uint32_t basis[32];
+    int r = 0;
+    for (int i = 0; i < n; ++i) {
+        uint32_t x = v[i];
+        for (int q = 0; q < r; ++q)
+            if ((x ^ basis[q]) < x) x ^= basis[q];
+        if (x) {
+            basis[r++] = x;
+            for (int q = r - 1; q > 0 && basis[q] > basis[q - 1]; --q) std::swap(basis[q], basis[q - 1]);
+        }
+    }
+    return r;
+}
+
+// Fills plan.orbit* when every input is a dim-permuted view of one parent and the output's fastest dim is moved
+// by at least one of the permutations (the transposing case).  `prog` is the matched recipe of the map plan.
+bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
+{
+    if (std::getenv("SB_NO_ORBIT")) return false;
+    const int n = c.ndim, nin = c.nops - 1, esz = dtype_size(c.ct);
+    if (c.op != OP_NONE || nin < 2 || nin > ORB_MAXIN || n < 2 || n > TMA_MAXRANK) return false;
+    if (c.ct != F32 && c.ct != F64) return false;
+    for (int k = 0; k <= nin; ++k)
+        if (c.dtype[k] != c.ct || c.conj[k]) return false;
+    for (int k = 2; k <= nin; ++k)
+        if (c.base[k] != c.base[1]) return false;
+    if (c.base[0] == c.base[1]) return false;
+    // parent dim order = input 1's strides ascending
+    int pord[MAXD];
+    for (int d = 0; d < n; ++d) {
+        pord[d] = d;
+        if (c.strides[1][d] <= 0 || c.strides[0][d] <= 0 || c.dims[d] >= ((int64_t)1 << 31)) return false;
+    }
+    std::stable_sort(pord, pord + n, [&](int a, int b) { return c.strides[1][a] < c.strides[1][b]; });
+    if (c.strides[1][pord[0]] != 1 || c.strides[0][0] != 1) return false;
+    for (int i = 1; i < n; ++i) {
+        const int64_t sp = c.strides[1][pord[i]], so = c.strides[0][i];
+        if (sp == c.strides[1][pord[i - 1]]) return false;
+        if ((sp * esz) % 16 != 0 || (so * esz) % 16 != 0) return false;
+        if (sp * esz >= ((int64_t)1 << 40) || so * esz >= ((int64_t)1 << 40)) return false;
+        if (so <= c.strides[0][i - 1]) return false;
+    }
+    // q[k][d]: parent position of canonical dim d under input k
+    int q[ORB_MAXIN + 1][MAXD];
+    for (int k = 1; k <= nin; ++k) {
+        bool used[MAXD] = {false};
+        for (int d = 0; d < n; ++d) {
+            int hit = -1;
+            for (int i = 0; i < n; ++i)
+                if (!used[i] && c.strides[1][pord[i]] == c.strides[k][d] && c.dims[pord[i]] == c.dims[d]) hit = i;
+            if (hit < 0) return false;
+            used[hit] = true;
+            q[k][d] = hit;
+        }
+    }
+    bool moved[MAXD] = {false};
+    int nmoved = 0;
+    for (int d = 0; d < n; ++d) {
+        for (int k = 2; k <= nin; ++k)
+            if (q[k][d] != q[1][d]) moved[d] = true;
+        nmoved += moved[d];
+    }
+    if (!moved[0] || nmoved < 2) return false;
+    // tile extents: 2^bb along every moved dim (a cube: the tile set must be closed under the permutations), batch
+    // bits along unmoved dims; 256*{4,8,16} elements, <= 16 KB (else <= 32 KB)
+    int cap[MAXD], tb[MAXD] = {0};
+    int capmin = 30;
+    for (int d = 0; d < n; ++d) {
+        cap[d] = ilog2_ceil(c.dims[d]);
+        if (moved[d]) capmin = std::min(capmin, cap[d]);
+    }
+    auto waste_of = [&](int d, int bits) {
+        const int64_t t = (int64_t)1 << bits;
+        return (double)(((c.dims[d] + t - 1) / t) * t) / (double)c.dims[d];
+    };
+    int bbmax = std::min(12 / nmoved, capmin);
+    for (;; --bbmax) {
+        if (bbmax < 1) return false;
+        double w = 1.0;
+        for (int d = 0; d < n; ++d)
+            if (moved[d]) w = std::max(w, waste_of(d, bbmax));
+        if (w <= 1.2) break;
+    }
+    int forced_bb = 0;
+    if (const char *e = std::getenv("SB_ORBIT_BITS")) forced_bb = std::atoi(e); // tuning knob: log2 cube edge
+    int ebits = 0;
+    bool found = false;
+    for (int pass = 0; pass < 2 && !found; ++pass) {
+        const int64_t limit = pass == 0 ? 16384 : 32768;
+        for (int bb = bbmax; bb >= 1 && !found; --bb) {
+            if (forced_bb > 0 && bb != forced_bb) continue;
+            if (((int64_t)esz << bb) < 32) break; // at least one 32-byte sector per box row
+            int eb = nmoved * bb;
+            if (eb > 12 || ((int64_t)esz << eb) > limit) continue;
+            int t2[MAXD] = {0};
+            for (int d = 0; d < n; ++d)
+                if (moved[d]) t2[d] = bb;
+            for (int d = 0; d < n && eb < 12; ++d) { // batch bits on unmoved dims (same box position in every view)
+                if (moved[d]) continue;
+                int add = 0;
+                while (eb + add < 12 && add < cap[d] && ((int64_t)esz << (eb + add + 1)) <= limit && waste_of(d, add + 1) <= 1.2) ++add;
+                t2[d] = add;
+                eb += add;
+            }
+            if (eb < 10) continue;
+            for (int d = 0; d < n; ++d) tb[d] = t2[d];
+            ebits = eb;
+            found = true;
+        }
+    }
+    if (!found) return false;
+    const int ept = 1 << (ebits - LOG_THREADS);
+    if (!orbit_instantiated(c.ct, prog.recipe, nin, ept)) return false;
+    const int32_t tile_bytes = esz << ebits;
+
+    // ---- work items: orbits of the tile grid under  c -> pb_1^-1(pb_k(c)) --------------------------------------
+    int64_t ntile[MAXD], ntiles = 1;
+    for (int d = 0; d < n; ++d) {
+        ntile[d] = (c.dims[d] + ((int64_t)1 << tb[d]) - 1) >> tb[d];
+        ntiles *= ntile[d];
+    }
+    if (ntiles < 2 || ntiles > (1 << 22)) return false;
+    auto decode = [&](int64_t id, int64_t *cc) {
+        for (int d = 0; d < n; ++d) {
+            cc[d] = id % ntile[d];
+            id /= ntile[d];
+        }
+    };
+    auto encode = [&](const int64_t *cc) {
+        int64_t id = 0;
+        for (int d = n - 1; d >= 0; --d) id = id * ntile[d] + cc[d];
+        return id;
+    };
+    int inv1[MAXD]; // parent position -> canonical dim under input 1
+    for (int d = 0; d < n; ++d) inv1[q[1][d]] = d;
+    auto image = [&](int k, const int64_t *cc, int64_t *nc) { // tile whose input-1 block is input k's block of tile cc
+        for (int d = 0; d < n; ++d) nc[inv1[q[k][d]]] = cc[d];
+    };
+    std::vector<uint8_t> seen((size_t)ntiles, 0);
+    std::vector<OrbitItem> items;
+    int gmax = 1;
+    std::vector<int64_t> orb;
+    for (int64_t t0 = 0; t0 < ntiles; ++t0) {
+        if (seen[(size_t)t0]) continue;
+        orb.assign(1, t0);
+        seen[(size_t)t0] = 1;
+        for (size_t h = 0; h < orb.size(); ++h) {
+            int64_t cc[MAXD], nc[MAXD];
+            decode(orb[h], cc);
+            for (int k = 2; k <= nin; ++k) {
+                image(k, cc, nc);
+                for (int d = 0; d < n; ++d)
+                    if (nc[d] >= ntile[d]) return false; // cannot happen: permuted dims have equal extents
+                const int64_t id = encode(nc);
+                if (!seen[(size_t)id]) {
+                    seen[(size_t)id] = 1;
+                    orb.push_back(id);
+                    if ((int)orb.size() > ORB_MAXG) return false;
+                }
+            }
+        }
+        OrbitItem it;
+        std::memset(&it, 0, sizeof it);
+        it.ntile = (int32_t)orb.size();
+        gmax = std::max(gmax, it.ntile);
+        for (int m = 0; m < it.ntile; ++m) {
+            int64_t cc[MAXD], nc[MAXD];
+            decode(orb[(size_t)m], cc);
+            for (int d = 0; d < n; ++d) it.ocrd[m][d] = (int32_t)(cc[d] << tb[d]);
+            for (int i = 0; i < n; ++i) it.pcrd[m][i] = (int32_t)(cc[pord[i]] << tb[pord[i]]);
+            for (int k = 1; k <= nin; ++k) {
+                if (k == 1) {
+                    it.slot[m][0] = (uint8_t)m;
+                    continue;
+                }
+                image(k, cc, nc);
+                const int64_t id = encode(nc);
+                int s = -1;
+                for (int z = 0; z < it.ntile; ++z)
+                    if (orb[(size_t)z] == id) s = z;
+                if (s < 0) return false;
+                it.slot[m][k - 1] = (uint8_t)s;
+            }
+        }
+        items.push_back(it);
+    }
+
+    // ---- thread map x = M u over GF(2): conflict-free shared-memory access for every view ----------------------
+    const int B = ebits, lg = esz == 4 ? 2 : 3;
+    const int L = esz == 4 ? 5 : 4; // lanes served together: a warp of 4-byte or a half-warp of 8-byte accesses
+    int xshift[MAXD], pshift[MAXD];
+    for (int d = 0, s = 0; d < n; ++d) {
+        xshift[d] = s;
+        s += tb[d];
+    }
+    for (int i = 0, s = 0; i < n; ++i) {
+        pshift[i] = s;
+        s += tb[pord[i]];
+    }
+    int ebit[ORB_MAXIN + 1][16]; // element-address bit of x-bit p under view v (0 = staging/output layout)
+    for (int d = 0; d < n; ++d)
+        for (int r = 0; r < tb[d]; ++r) {
+            const int p = xshift[d] + r;
+            ebit[0][p] = p;
+            for (int k = 1; k <= nin; ++k) ebit[k][p] = pshift[q[k][d]] + r;
+        }
+    auto restricted = [&](int v, uint32_t m) {
+        uint32_t r = 0;
+        for (int p = 0; p < B; ++p)
+            if (((m >> p) & 1u) && ebit[v][p] < L) r ^= 1u << ebit[v][p];
+        return r;
+    };
+    uint32_t col[16];
+    bool ok = false;
+    uint64_t rng = 0x9E3779B97F4A7C15ull;
+    for (int attempt = 0; attempt < 256 && !ok; ++attempt) {
+        int nc = 0;
+        bool stuck = false;
+        while (nc < L && !stuck) {
+            bool got = false;
+            for (int tries = 0; tries < 4096 && !got; ++tries) {
+                rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                uint32_t cand = (uint32_t)(rng >> 33) & ((1u << B) - 1u);
+                if (attempt == 0 && tries < B) cand = 1u << tries; // unit vectors first: the identity map when it already works
+                if (!cand) continue;
+                col[nc] = cand;
+                bool good = gf2_rank(col, nc + 1) == nc + 1;
+                for (int v = 0; v <= nin && good; ++v) {
+                    uint32_t rv[8];
+                    for (int z = 0; z <= nc; ++z) rv[z] = restricted(v, col[z]);
+                    good = gf2_rank(rv, nc + 1) == nc + 1;
+                }
+                got = good;
+            }
+            if (got) ++nc;
+            else stuck = true;
+        }
+        ok = !stuck;
+    }
+    if (!ok) return false;
+    int ncol = L;
+    for (int p = 0; p < B && ncol < B; ++p) { // complete to a basis with unit vectors
+        col[ncol] = 1u << p;
+        if (gf2_rank(col, ncol + 1) == ncol + 1) ++ncol;
+    }
+    if (ncol != B) return false;
+
+    OrbitParams &O = plan.orbit;
+    std::memset(&O, 0, sizeof O);
+    O.nin = nin;
+    O.rank = n;
+    O.tile_bytes = tile_bytes;
+    O.gmax = gmax;
+    O.stage_bytes = gmax * tile_bytes;
+    O.ept = ept;
+    O.nitems = (int32_t)items.size();
+    O.prog = prog;
+    auto addr_image = [&](int v, uint32_t m) {
+        uint32_t a = 0;
+        for (int p = 0; p < B; ++p)
+            if ((m >> p) & 1u) a ^= (uint32_t)1 << (ebit[v][p] + lg);
+        return a;
+    };
+    for (int v = 0; v <= nin; ++v) {
+        for (int i = 0; i < LOG_THREADS; ++i) O.tcol[v][i] = addr_image(v, col[i]);
+        for (int j = 0; j < ept; ++j) {
+            uint32_t a = 0;
+            for (int i = 0; i + LOG_THREADS < B; ++i)
+                if ((j >> i) & 1) a ^= addr_image(v, col[LOG_THREADS + i]);
+            O.jtab[v][j] = a;
+        }
+    }
+    // guard: the bank model must agree (every warp access of every view is conflict-free)
+    for (int v = 0; v <= nin; ++v)
+        for (int w = 0; w < THREADS / 32; ++w)
+            for (int j = 0; j < ept; ++j) {
+                int32_t ea[32];
+                for (int l = 0; l < 32; ++l) {
+                    uint32_t a = O.jtab[v][j];
+                    const int t = w * 32 + l;
+                    for (int i = 0; i < LOG_THREADS; ++i)
+                        if ((t >> i) & 1) a ^= O.tcol[v][i];
+                    ea[l] = (int32_t)(a >> lg);
+                }
+                if (smem_wavefronts(ea, 32, esz) != (esz == 4 ? 1 : 2)) return false;
+            }
+    // ring depth: as many stages as fit beside the two staging buffers (<= 4); small stages leave room for 2 CTAs/SM
+    int ns = (int)((176 * 1024 - 2 * (int64_t)tile_bytes) / O.stage_bytes);
+    ns = std::max(1, std::min(4, ns));
+    if (const char *e = std::getenv("SB_ORBIT_STAGES")) {
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= 8) ns = v;
+    }
+    O.nstage = ns;
+    plan.orbit_smem_bytes = (int64_t)ns * O.stage_bytes + 2 * (int64_t)tile_bytes + 128;
+    if (plan.orbit_smem_bytes > 224 * 1024) return false;
+    Plan::TmaGlobal &gp = plan.orbit_global[0], &go = plan.orbit_global[1];
+    gp = Plan::TmaGlobal{};
+    go = Plan::TmaGlobal{};
+    gp.rank = go.rank = n;
+    gp.elem_bytes = go.elem_bytes = esz;
+    for (int i = 0; i < n; ++i) {
+        gp.gdim[i] = (uint64_t)c.dims[pord[i]];
+        gp.gstride_bytes[i] = (uint64_t)c.strides[1][pord[i]] * (uint64_t)esz;
+        gp.box[i] = 1u << tb[pord[i]];
+        go.gdim[i] = (uint64_t)c.dims[i];
+        go.gstride_bytes[i] = (uint64_t)c.strides[0][i] * (uint64_t)esz;
+        go.box[i] = 1u << tb[i];
+    }
+    for (int d = 0; d < MAXD; ++d) plan.orbit_tile_b[d] = d < n ? (1 << tb[d]) : 0;
+    plan.orbit_items = std::move(items);
+    plan.orbit_ok = true;
+    return true;
+}
+
 int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err)
 {
     MapParams &P = plan.map;
@@ -1032,6 +1363,7 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
     }
     plan.elements = 1;
     for (int i = 0; i < n; ++i) plan.elements *= c.dims[i];
+    if (uniform && plan_orbit(c, P.prog, plan)) plan.note = "alias-fused orbits";
     return SB_OK;
 }
 
@@ -1272,6 +1604,12 @@ std::string describe_plan(const Plan &p)
         const MapParams &P = p.map;
         arr64("dims", P.dims, P.ndim);
         arr32("tile", P.tile_b, P.ndim);
+        if (p.orbit_ok) {
+            os << ",\"orbit\":{\"items\":" << p.orbit.nitems << ",\"gmax\":" << p.orbit.gmax << ",\"ept\":" << p.orbit.ept
+               << ",\"nstage\":" << p.orbit.nstage << ",\"tile_bytes\":" << p.orbit.tile_bytes << ",\"smem_bytes\":" << p.orbit_smem_bytes;
+            arr32("tile", p.orbit_tile_b, P.ndim);
+            os << "}";
+        }
         os << ",\"ntiles\":" << P.ntiles << ",\"tile_order\":" << (p.tile_order.empty() ? 0 : 1) << ",\"tma\":" << (p.tma_ok ? p.tma.nstage : 0) << ",\"nstaged\":" << P.nstaged << ",\"staged\":[";
         for (int k = 0; k < P.nops; ++k) os << (k ? "," : "") << (int)P.staged[k];
         os << "],\"strides\":[";

@@ -52,6 +52,14 @@ struct Plan {
     } tma_global[TMA_MAXIN];
     int64_t tma_smem_bytes = 0;
     std::vector<TileDesc> tile_desc; // per-tile records in launch order (uploaded with the plan)
+    // alias-fused ("orbit") variant: all inputs are permuted views of one parent (see common.hpp).  Preferred over the
+    // TMA ring when available; needs 16-byte aligned bases and an output that does not overlap the parent (bind time).
+    bool orbit_ok = false;
+    OrbitParams orbit{};
+    TmaGlobal orbit_global[2];           // [0] parent (load), [1] output (store)
+    std::vector<OrbitItem> orbit_items;  // work items in launch order (uploaded with the plan)
+    int64_t orbit_smem_bytes = 0;
+    int orbit_tile_b[MAXD] = {0};
     std::string note;
 };
 

@@ -9,6 +9,7 @@
 #include "../../strided.jl_b200/csrc/reduce_tile.hpp"
 #include "../../strided.jl_b200/csrc/planner.hpp"
 #include "../../strided.jl_b200/csrc/tma_tile.hpp"
+#include "../../strided.jl_b200/csrc/orbit_tile.hpp"
 #include <cstdlib>
 
 #include <cstring>
@@ -91,6 +92,75 @@ template <class CT, int RC, int NIN, int EPT> static void run_tma(const Plan &pl
                 tma_consume<CT, RC, NIN, EPT>(P, T, th[t], th0[t], tl, t, stage);
             }
         }
+}
+
+// Alias-fused orbit variant: the TMA box loads of the parent blocks (dense box in parent dim order, zero-filled out of
+// bounds) and the TMA store of the staged output tile (clipped) are emulated; the real consumer body runs per thread.
+static void emul_box(const Plan::TmaGlobal &g, const int32_t *crd, unsigned char *gbase, unsigned char *sm, bool store)
+{
+    int64_t nelem = 1;
+    for (int i = 0; i < g.rank; ++i) nelem *= g.box[i];
+    for (int64_t e = 0; e < nelem; ++e) {
+        int64_t rest = e, off = 0;
+        bool oob = false;
+        for (int i = 0; i < g.rank; ++i) {
+            const int64_t ix = rest % g.box[i];
+            rest /= g.box[i];
+            const int64_t gi = (int64_t)crd[i] + ix;
+            if (gi < 0 || gi >= (int64_t)g.gdim[i]) oob = true;
+            off += gi * (i == 0 ? (int64_t)g.elem_bytes : (int64_t)g.gstride_bytes[i]);
+        }
+        unsigned char *s = sm + e * g.elem_bytes;
+        if (store) {
+            if (!oob) std::memcpy(gbase + off, s, (size_t)g.elem_bytes);
+        } else {
+            if (oob) std::memset(s, 0, (size_t)g.elem_bytes);
+            else std::memcpy(s, gbase + off, (size_t)g.elem_bytes);
+        }
+    }
+}
+
+template <class CT, int RC, int NIN, int EPT> static void run_orbit(const Plan &plan, int grid)
+{
+    const OrbitParams &O = plan.orbit;
+    std::vector<unsigned char> ring((size_t)O.nstage * O.stage_bytes + 2 * (size_t)O.tile_bytes);
+    std::vector<OrbitThread<NIN>> th(THREADS);
+    for (int t = 0; t < THREADS; ++t) orbit_thread_init<NIN>(O, t, th[t]);
+    const uint32_t staging0 = (uint32_t)(O.nstage * O.stage_bytes);
+    for (int b = 0; b < grid; ++b) {
+        int stage = 0;
+        uint32_t nout = 0;
+        for (uint32_t pos = (uint32_t)b; pos < (uint32_t)O.nitems; pos += (uint32_t)grid) {
+            const OrbitItem &it = plan.orbit_items[pos];
+            std::memset(ring.data() + (size_t)stage * O.stage_bytes, 0xCD, (size_t)O.stage_bytes);
+            for (int s = 0; s < it.ntile; ++s)
+                emul_box(plan.orbit_global[0], it.pcrd[s], plan.map.base[1], ring.data() + (size_t)stage * O.stage_bytes + (size_t)s * O.tile_bytes, false);
+            for (int m = 0; m < it.ntile; ++m) {
+                uint32_t slots;
+                std::memcpy(&slots, it.slot[m], 4);
+                const uint32_t sbuf_off = staging0 + (nout & 1u) * (uint32_t)O.tile_bytes;
+                for (int t = 0; t < THREADS; ++t)
+                    orbit_compute<CT, RC, NIN, EPT>(O, th[t], ring.data(), (uint32_t)(stage * O.stage_bytes), slots, sbuf_off);
+                emul_box(plan.orbit_global[1], it.ocrd[m], plan.map.base[0], ring.data() + sbuf_off, true);
+                ++nout;
+            }
+            if (++stage == O.nstage) stage = 0;
+        }
+    }
+}
+
+template <class CT> static bool orbit_dispatch(const Plan &plan, int grid)
+{
+    const int rc = plan.key.recipe, nin = plan.orbit.nin, ept = plan.orbit.ept;
+#define TRYO(R, N)                                                                                                   \
+    if (rc == R && nin == N) {                                                                                       \
+        if (ept == 4) { run_orbit<CT, R, N, 4>(plan, grid); return true; }                                           \
+        if (ept == 8) { run_orbit<CT, R, N, 8>(plan, grid); return true; }                                           \
+        if (ept == 16) { run_orbit<CT, R, N, 16>(plan, grid); return true; }                                         \
+    }
+    TRYO(RC_ADD2, 2) TRYO(RC_ADD2_MUL, 2) TRYO(RC_ADD2_DIV, 2) TRYO(RC_AXPY, 2) TRYO(RC_AXPBY, 2) TRYO(RC_SUM3, 3) TRYO(RC_SUM4, 4)
+#undef TRYO
+    return false;
 }
 
 template <class CT> static bool tma_dispatch(const Plan &plan, int grid)
@@ -216,6 +286,15 @@ extern "C" int emul_mapreduce(const sb_desc *desc, int grid_limit)
     if (plan.kind == PLAN_MAP) {
         int grid = (int)plan.grid;
         if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;
+        if (plan.orbit_ok && !std::getenv("SB_EMUL_NO_ORBIT")) {
+            bool aligned = ((reinterpret_cast<uintptr_t>(plan.map.base[0]) | reinterpret_cast<uintptr_t>(plan.map.base[1])) & 15u) == 0;
+            if (aligned) {
+                int g2 = (int)std::min<int64_t>(plan.orbit.nitems, 148);
+                if (grid_limit > 0 && g2 > grid_limit) g2 = grid_limit;
+                ok = plan.key.ct == F32 ? orbit_dispatch<float>(plan, g2) : plan.key.ct == F64 ? orbit_dispatch<double>(plan, g2) : false;
+                if (ok) return SB_OK;
+            }
+        }
         if (plan.tma_ok && !std::getenv("SB_EMUL_NO_TMA")) {
             bool aligned = true;
             for (int k = 1; k < plan.map.nops; ++k) aligned = aligned && ((reinterpret_cast<uintptr_t>(plan.map.base[k]) & 15u) == 0);

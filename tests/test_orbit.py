@@ -1,0 +1,101 @@
+"""Alias-fused ("orbit") map path: every input is a dim-permuted view of ONE parent (`(A .+ A') ./ 2`, the 4-way
+permutedims sum of README.md:91-104, reference src/mapreduce.jl:11-14 + src/broadcast.jl:27-37).
+
+CPU part: the planner must pick the path for these shapes and the thread-grid emulation (TMA box load/store emulated,
+real consumer body) must reproduce the NumPy semantic oracle bit for bit.  GPU part: the same cases plus the BASELINE
+sizes through the C ABI, bit-exact against the oracle."""
+import numpy as np
+import pytest
+
+from helpers import A, F, K, Case, ViewSpec, SEED, randn, case_c2, case_c4, P_SUM4
+
+
+def _dense_pair(shape, dt, seed=SEED):
+    rng = np.random.default_rng(seed)
+    n = int(np.prod(shape))
+    return randn(rng, n, dt), np.zeros(n, dt)
+
+
+def orbit_cases(big=False):
+    """(case, must_use_orbit); `big` adds the sizes of the reference's tests (1000 x 1000) for the GPU run"""
+    s = lambda n: n  # noqa: E731
+    out = []
+    for dt in (np.float32, np.float64):
+        nm = np.dtype(dt).name
+        # C2 family: A + A' (edge tiles: sizes that are not multiples of 32)
+        for n in (64, 260, 250) + ((1000,) if big else ()):
+            c = case_c2(n, dt)
+            c.name = f"orbit_avg_{nm}_{n}"
+            out.append((c, (n * np.dtype(dt).itemsize) % 16 == 0 and n >= 260))
+        # input 1 is itself the transposed view: B = A' + A (parent order != output order)
+        n = s(96)
+        a, b = _dense_pair((n, n), dt)
+        Av = ViewSpec.dense(1, (n, n))
+        out.append((Case(f"orbit_add2_tfirst_{nm}", [b, a], [ViewSpec.dense(0, (n, n)), Av.permutedims((1, 0)), Av],
+                         [A(0), A(1), F("add")]), True))
+        # axpby with a transposed alias: B = 2*A + 0.5*A'
+        out.append((Case(f"orbit_axpby_{nm}", [b.copy(), a], [ViewSpec.dense(0, (n, n)), Av, Av.permutedims((1, 0))],
+                         [K(2), A(0), F("mul"), K(0.5), A(1), F("mul"), F("add")]), True))
+        # batched: B[i,j,z] = A[i,j,z] + A[j,i,z]  (unmoved batch dim)
+        n, z = 48, 8
+        a, b = _dense_pair((n, n, z), dt)
+        Av = ViewSpec.dense(1, (n, n, z))
+        out.append((Case(f"orbit_batched_{nm}", [b, a], [ViewSpec.dense(0, (n, n, z)), Av, Av.permutedims((1, 0, 2))],
+                         [A(0), A(1), F("add")]), True))
+        # 3-cycle: A[i,j,k] + A[j,k,i] + A[k,i,j]
+        n = 32
+        a, b = _dense_pair((n,) * 3, dt)
+        Av = ViewSpec.dense(1, (n,) * 3)
+        out.append((Case(f"orbit_sum3_{nm}", [b, a], [ViewSpec.dense(0, (n,) * 3), Av, Av.permutedims((1, 2, 0)), Av.permutedims((2, 0, 1))],
+                         [A(0), A(1), F("add"), A(2), F("add")]), True))
+        # C4 family (edge tiles for 20)
+        for n in (16, 20):
+            c = case_c4(n, dt)
+            c.name = f"orbit_sum4_{nm}_{n}"
+            out.append((c, True))
+        # 4-D pair swap: A[i,j,k,l] + A[j,i,l,k]  (two independent 2-cycles)
+        n = 16
+        a, b = _dense_pair((n,) * 4, dt)
+        Av = ViewSpec.dense(1, (n,) * 4)
+        out.append((Case(f"orbit_pairswap_{nm}", [b, a], [ViewSpec.dense(0, (n,) * 4), Av, Av.permutedims((1, 0, 3, 2))],
+                         [A(0), A(1), F("add")]), True))
+    return out
+
+
+_CPU = orbit_cases()
+
+
+@pytest.mark.parametrize("case,must", _CPU, ids=[c.name for c, _ in _CPU])
+def test_orbit_emulated(case, must):
+    plan = case.plan()
+    if must:
+        assert "orbit" in plan, plan
+        o = plan["orbit"]
+        assert o["ept"] in (4, 8, 16) and o["gmax"] <= 4 and o["smem_bytes"] <= 224 * 1024
+    want = case.expected()
+    case.assert_close(case.run_emul(), want, exact=True)
+    case.assert_close(case.run_emul(grid_limit=2), want, exact=True)  # few persistent CTAs: ring wrap-around, staging parity
+
+
+def test_orbit_not_chosen_when_output_aliases_parent_or_rows_unaligned():
+    # in-place A .= A + A' is undefined for a parallel engine; the plan must not fuse it
+    n = 64
+    rng = np.random.default_rng(SEED)
+    a = randn(rng, n * n, np.float64)
+    Av = ViewSpec.dense(0, (n, n))
+    c = Case("inplace", [a], [Av, Av, Av.permutedims((1, 0))], [A(0), A(1), F("add")])
+    assert "orbit" not in c.plan()
+    # row pitch 97*8 bytes is not a multiple of 16: not TMA-describable
+    assert "orbit" not in case_c2(97).plan()
+    # the BASELINE shapes do use it
+    for c in (case_c2(4000), case_c4(64), case_c4(32, np.float64)):
+        assert "orbit" in c.plan(), c.name
+
+
+_GPU = orbit_cases(big=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,must", _GPU, ids=[c.name for c, _ in _GPU])
+def test_orbit_gpu(case, must):
+    case.assert_close(case.run_gpu("device"), exact=True)
