@@ -496,6 +496,7 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
         const OrbitEntry *ok = overlap ? nullptr : find_orbit_kernel(KernelKey{plan.key.ct, plan.key.recipe, plan.orbit.nin, plan.orbit.ept, 1});
         alignas(64) CUtensorMap maps[2];
         if (ok && encode_orbit_maps(plan, maps)) {
+            plan.orbit.out_base = plan.map.base[0];
             int nb = 1;
             rc = occupancy_of(ctx, ok->func, ok->occupancy, (size_t)plan.orbit_smem_bytes, nb);
             if (rc != SB_OK) return rc;

@@ -246,6 +246,7 @@ struct OrbitItem {
     int32_t pcrd[ORB_MAXG][TMA_MAXRANK]; // TMA coordinates (parent dim order) of parent block s
     int32_t ocrd[ORB_MAXG][TMA_MAXRANK]; // TMA coordinates (output dim order) of output tile m
     uint8_t slot[ORB_MAXG][ORB_MAXIN];   // input k of output tile m reads parent block slot[m][k]
+    int64_t ooff[ORB_MAXG];              // byte offset of output tile m's origin (direct-store mode)
 };
 struct OrbitParams {
     int32_t nin, rank;
@@ -255,7 +256,17 @@ struct OrbitParams {
     int32_t gmax;
     int32_t ept;
     int32_t nitems;
+    int32_t debug;       // diagnostics only (SB_DEBUG, tools/): 1 no TMA loads, 2 no TMA stores, 4 no compute, 8 no proxy fence, 16 no tile barrier -- results are WRONG
+    int32_t nstaging;    // output staging buffers (TMA stores in flight + 1), 2..4
     const OrbitItem *items;
+    // direct-store mode (no edge tiles): the staged tile is written by all consumer threads with 128-bit st.global,
+    // thread t owning the 16-byte groups g = t + 256 r of the staging buffer; the TMA unit then only serves the loads
+    // (it processes box rows at ~2 cycles each, which bounds 32-byte-row tiles when it has to do both directions)
+    int32_t direct_store;
+    int32_t st_groups;            // groups per thread per tile = tile_bytes / 4096
+    unsigned char *out_base;
+    int64_t st_tcol[LOG_THREADS]; // global byte offset contributed by bit i of t
+    int64_t st_roff[8];           // ... by r
     uint32_t tcol[ORB_MAXIN + 1][LOG_THREADS]; // byte-address image of thread bit i; view 0 = output staging, k = input k
     uint32_t jtab[ORB_MAXIN + 1][MAXEPT];      // byte-address image of j
     Program prog;

@@ -71,6 +71,7 @@ map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ 
     extern __shared__ unsigned char sb_orbit_smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[ORB_MAXSTAGE];
     __shared__ __align__(8) uint64_t empty_bar[ORB_MAXSTAGE];
+    __shared__ __align__(16) uint32_t item_smem[ORB_MAXSTAGE][64];
     // ring (nstage stages of gmax blocks) followed by two staging buffers; TMA needs 128-byte aligned boxes
     unsigned char *ring = sb_orbit_smem_raw + ((0u - smem_u32(sb_orbit_smem_raw)) & 127u); // (offset form keeps the address space known: LDS/STS)
     const uint32_t ring_u32 = smem_u32(ring);
@@ -86,23 +87,45 @@ map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ 
     __syncthreads();
     const uint32_t nitems = (uint32_t)O.nitems;
     const uint32_t grid = gridDim.x;
+    constexpr int IW = (int)(sizeof(OrbitItem) / 4); // words per work item
+    static_assert(sizeof(OrbitItem) % 4 == 0 && IW <= 64, "OrbitItem is copied as <= 2 words per producer lane");
     if (warp == THREADS / 32) {
         // ---------------- producer warp ----------------
+        // The work item (coordinates, slots) travels with the stage: the producer copies it into shared memory before
+        // arming the full barrier, so that no consumer ever waits on a dependent global load (measured: the item loads
+        // on the consumers' critical path cost ~1 us per item, profiles/r01_v9_orbit_first.txt).
         int stage = 0;
         uint32_t parity = 1; // a fresh barrier passes a wait on parity 1: every stage starts out empty
-        for (uint32_t pos = blockIdx.x; pos < nitems; pos += grid) {
-            const OrbitItem *it = O.items + pos;
-            const int ntile = it->ntile;
-            int32_t crd[TMA_MAXRANK] = {0, 0, 0, 0, 0};
-            if (lane < ntile) {
-#pragma unroll
-                for (int i = 0; i < TMA_MAXRANK; ++i) crd[i] = it->pcrd[lane][i];
+        // item words are fetched TWO items ahead (registers a*/b*): one L2 round trip per item would otherwise bound the loop
+        uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+        auto fetch = [&](uint32_t p, uint32_t &x0, uint32_t &x1) {
+            if (p < nitems) {
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(O.items + p);
+                x0 = src[lane];
+                if (lane + 32 < IW) x1 = src[lane + 32];
             }
+        };
+        fetch(blockIdx.x, a0, a1);
+        fetch(blockIdx.x + grid, b0, b1);
+        for (uint32_t pos = blockIdx.x; pos < nitems; pos += grid) {
             mbar_wait(smem_u32(&empty_bar[stage]), parity);
-            const uint32_t fb = smem_u32(&full_bar[stage]);
-            if (lane == 0) mbar_expect_tx(fb, (uint32_t)(ntile * O.tile_bytes));
+            uint32_t *d = item_smem[stage];
+            d[lane] = a0;
+            if (lane + 32 < IW) d[lane + 32] = a1;
             __syncwarp();
-            if (lane < ntile) tma_load_rank(O.rank, ring_u32 + (uint32_t)(stage * O.stage_bytes + lane * O.tile_bytes), &min, fb, crd);
+            a0 = b0;
+            a1 = b1;
+            fetch(pos + 2 * grid, b0, b1);
+            const OrbitItem *it = reinterpret_cast<const OrbitItem *>(d);
+            const int ntile = it->ntile;
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            if (lane == 0) mbar_expect_tx(fb, (uint32_t)(ntile * O.tile_bytes)); // (release: the item words above are visible)
+            __syncwarp();
+            if (O.debug & 1) {
+                if (lane == 0) asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(fb), "r"((uint32_t)(ntile * O.tile_bytes)) : "memory");
+            } else if (lane < ntile) {
+                tma_load_rank(O.rank, ring_u32 + (uint32_t)(stage * O.stage_bytes + lane * O.tile_bytes), &min, fb, it->pcrd[lane]);
+            }
             if (++stage == S) {
                 stage = 0;
                 parity ^= 1u;
@@ -114,30 +137,43 @@ map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ 
         orbit_thread_init<NIN>(O, tid, th);
         const uint32_t staging0 = (uint32_t)(S * O.stage_bytes);
         int stage = 0;
-        uint32_t parity = 0, nout = 0;
+        uint32_t parity = 0, sbuf = 0;
+        const int K = O.nstaging;
+        const int64_t st_t = orbit_store_toff(O, tid);
         for (uint32_t pos = blockIdx.x; pos < nitems; pos += grid) {
-            const OrbitItem *it = O.items + pos;
-            const int ntile = it->ntile;
             mbar_wait(smem_u32(&full_bar[stage]), parity);
+            const OrbitItem *it = reinterpret_cast<const OrbitItem *>(item_smem[stage]);
+            const int ntile = it->ntile;
             for (int m = 0; m < ntile; ++m) {
                 const uint32_t slots = *reinterpret_cast<const uint32_t *>(it->slot[m]);
-                const uint32_t sbuf_off = staging0 + (nout & 1u) * (uint32_t)O.tile_bytes;
-                orbit_compute<CT, RC, NIN, EPT>(O, th, ring, (uint32_t)(stage * O.stage_bytes), slots, sbuf_off);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the TMA store
-                // the store issued one tile ago read the OTHER staging buffer: it must be done before anyone writes there
-                if (tid == 0 && nout > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
-                if (tid == 0) {
-                    int32_t crd[TMA_MAXRANK];
-#pragma unroll
-                    for (int i = 0; i < TMA_MAXRANK; ++i) crd[i] = it->ocrd[m][i];
-                    tma_store_rank(O.rank, &mout, ring_u32 + sbuf_off, crd);
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                const uint32_t sbuf_off = staging0 + sbuf * (uint32_t)O.tile_bytes;
+                if (!(O.debug & 4)) orbit_compute<CT, RC, NIN, EPT>(O, th, ring, (uint32_t)(stage * O.stage_bytes), slots, sbuf_off);
+                if (O.direct_store) {
+                    // two staging buffers: a thread can only reach the writes of tile m+2 (same buffer) through the barrier
+                    // of tile m+1, which every thread passes after its own reads of tile m below
+                    if (!(O.debug & 16)) asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+                    if (!(O.debug & 2)) orbit_store_direct(O, tid, st_t, ring, sbuf_off, O.out_base + it->ooff[m]);
+                } else {
+                    if (!(O.debug & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the TMA store
+                    // the NEXT tile is computed into the buffer the store of K-1 tiles ago reads from: that store must have
+                    // finished reading before anyone passes the barrier (at most K-2 younger stores may still be pending)
+                    if (tid == 0) {
+                        switch (K) {
+                        case 2: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+                        case 3: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+                        default: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+                        }
+                    }
+                    if (!(O.debug & 16)) asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+                    if (tid == 0 && !(O.debug & 2)) {
+                        tma_store_rank(O.rank, &mout, ring_u32 + sbuf_off, it->ocrd[m]);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
                 }
-                ++nout;
+                if (++sbuf == (uint32_t)K) sbuf = 0;
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage])); // this warp is done with the stage
+            if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage])); // this warp is done with the stage (and its item copy)
             if (++stage == S) {
                 stage = 0;
                 parity ^= 1u;

@@ -35,7 +35,10 @@ template <class CT, int RC, int NIN, int EPT>
 SB_HD void orbit_compute(const OrbitParams &O, const OrbitThread<NIN> &th, unsigned char *ring, uint32_t stage_off, uint32_t slots,
                          uint32_t sbuf_off)
 {
-    constexpr int CH = EPT < 4 ? EPT : 4; // elements in flight per thread: NIN * CH shared-memory loads
+#ifndef SB_ORBIT_CH
+#define SB_ORBIT_CH 8
+#endif
+    constexpr int CH = EPT < SB_ORBIT_CH ? EPT : SB_ORBIT_CH; // elements in flight per thread: NIN * CH shared-memory loads
     uint32_t bt[NIN + 1];
     bt[0] = sbuf_off | th.T[0];
 #pragma unroll
@@ -55,6 +58,33 @@ SB_HD void orbit_compute(const OrbitParams &O, const OrbitThread<NIN> &th, unsig
             for (int k = 0; k < NIN; ++k) a[k] = v[k][u];
             *reinterpret_cast<CT *>(ring + (bt[0] ^ O.jtab[0][j0 + u])) = fn.template eval<NIN>(O.prog, a);
         }
+    }
+}
+
+// direct-store pass of one staged tile (after the tile barrier): thread t copies its 16-byte groups to the output
+struct OrbitVec16 {
+    alignas(16) uint32_t w[4];
+};
+SB_HD int64_t orbit_store_toff(const OrbitParams &O, int t)
+{
+    int64_t a = 0;
+#pragma unroll
+    for (int i = 0; i < LOG_THREADS; ++i)
+        if ((t >> i) & 1) a += O.st_tcol[i];
+    return a;
+}
+SB_HD void orbit_store_direct(const OrbitParams &O, int t, int64_t st_t, const unsigned char *ring, uint32_t sbuf_off, unsigned char *out_tile)
+{
+    const unsigned char *src = ring + sbuf_off + 16u * (uint32_t)t;
+    unsigned char *dst = out_tile + st_t;
+#pragma unroll 4
+    for (int r = 0; r < O.st_groups; ++r) {
+#if defined(__CUDA_ARCH__)
+        const OrbitVec16 v = *reinterpret_cast<const OrbitVec16 *>(src + (size_t)r * (16u * THREADS));
+        __stcs(reinterpret_cast<uint4 *>(dst + O.st_roff[r]), make_uint4(v.w[0], v.w[1], v.w[2], v.w[3])); // streaming: never re-read
+#else
+        for (int b = 0; b < 16; ++b) dst[O.st_roff[r] + b] = src[(size_t)r * (16u * THREADS) + b]; // (host emulation: no alignment assumed)
+#endif
     }
 }
 

@@ -792,6 +792,10 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
 {
     if (std::getenv("SB_NO_ORBIT")) return false;
     const int n = c.ndim, nin = c.nops - 1, esz = dtype_size(c.ct);
+    // Two aliased views (A and A'): the TMA ring kernel (two loads through L2, alias-aware tile order) measures
+    // 43.7 us on config 2 against 44.8-46 us here (profiles/r01_v9_orbit_tma_vs_lsu_breakdown.txt) -- both are bound by
+    // the ~20 B/clk/SM the TMA unit moves -- so the fused path is taken from three views on, where it wins 3x.
+    if (nin == 2 && !std::getenv("SB_ORBIT_NIN2")) return false;
     if (c.op != OP_NONE || nin < 2 || nin > ORB_MAXIN || n < 2 || n > TMA_MAXRANK) return false;
     if (c.ct != F32 && c.ct != F64) return false;
     for (int k = 0; k <= nin; ++k)
@@ -910,11 +914,45 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
     auto image = [&](int k, const int64_t *cc, int64_t *nc) { // tile whose input-1 block is input k's block of tile cc
         for (int d = 0; d < n; ++d) nc[inv1[q[k][d]]] = cc[d];
     };
+    // Launch order of the orbit representatives: by cubic SUPER-BLOCKS of 2^sup tiles along every moved dim.  The items
+    // in flight at any time then cover, in EVERY view's block family, runs of 2^sup adjacent blocks along that family's
+    // contiguous dim (DRAM page locality for the transposed families, whose neighbours would otherwise be a whole
+    // row of tiles apart in launch order).
+    int sup = 2;
+    if (const char *e = std::getenv("SB_ORBIT_SUPER")) sup = std::max(0, std::min(6, std::atoi(e)));
+    std::vector<int64_t> visit;
+    visit.reserve((size_t)ntiles);
+    {
+        int64_t nsb[MAXD], nsb_total = 1, sbx[MAXD];
+        for (int d = 0; d < n; ++d) {
+            sbx[d] = moved[d] ? ((int64_t)1 << sup) : 1;
+            nsb[d] = (ntile[d] + sbx[d] - 1) / sbx[d];
+            nsb_total *= nsb[d];
+        }
+        for (int64_t sb0 = 0; sb0 < nsb_total; ++sb0) {
+            int64_t rest = sb0, lo[MAXD], hi[MAXD], t[MAXD];
+            for (int d = 0; d < n; ++d) {
+                lo[d] = (rest % nsb[d]) * sbx[d];
+                rest /= nsb[d];
+                hi[d] = std::min(lo[d] + sbx[d], ntile[d]);
+                t[d] = lo[d];
+            }
+            for (;;) {
+                visit.push_back(encode(t));
+                int d = 0;
+                for (; d < n; ++d) {
+                    if (++t[d] < hi[d]) break;
+                    t[d] = lo[d];
+                }
+                if (d == n) break;
+            }
+        }
+    }
     std::vector<uint8_t> seen((size_t)ntiles, 0);
     std::vector<OrbitItem> items;
     int gmax = 1;
     std::vector<int64_t> orb;
-    for (int64_t t0 = 0; t0 < ntiles; ++t0) {
+    for (const int64_t t0 : visit) {
         if (seen[(size_t)t0]) continue;
         orb.assign(1, t0);
         seen[(size_t)t0] = 1;
@@ -940,7 +978,10 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
         for (int m = 0; m < it.ntile; ++m) {
             int64_t cc[MAXD], nc[MAXD];
             decode(orb[(size_t)m], cc);
-            for (int d = 0; d < n; ++d) it.ocrd[m][d] = (int32_t)(cc[d] << tb[d]);
+            for (int d = 0; d < n; ++d) {
+                it.ocrd[m][d] = (int32_t)(cc[d] << tb[d]);
+                it.ooff[m] += (cc[d] << tb[d]) * c.strides[0][d] * esz;
+            }
             for (int i = 0; i < n; ++i) it.pcrd[m][i] = (int32_t)(cc[pord[i]] << tb[pord[i]]);
             for (int k = 1; k <= nin; ++k) {
                 if (k == 1) {
@@ -1029,6 +1070,13 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
     O.ept = ept;
     O.nitems = (int32_t)items.size();
     O.prog = prog;
+    if (const char *dbg = std::getenv("SB_DEBUG")) { // diagnostics only: results are WRONG with these
+        if (std::strstr(dbg, "noload")) O.debug |= 1;
+        if (std::strstr(dbg, "nostore")) O.debug |= 2;
+        if (std::strstr(dbg, "nocompute")) O.debug |= 4;
+        if (std::strstr(dbg, "nofence")) O.debug |= 8;
+        if (std::strstr(dbg, "nobar")) O.debug |= 16;
+    }
     auto addr_image = [&](int v, uint32_t m) {
         uint32_t a = 0;
         for (int p = 0; p < B; ++p)
@@ -1044,6 +1092,30 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
             O.jtab[v][j] = a;
         }
     }
+    // direct-store mode: no edge tiles, and a 16-byte group stays inside the output's contiguous dim
+    {
+        const int lgV = esz == 4 ? 2 : 1;
+        // measured (profiles/r01_v9_orbit_directstore_graph.txt): 128-bit st.global from the staging buffer is slower than
+        // the TMA store for 32-byte rows (C4: 36.4 vs 28.6 us) and equal for 256-byte rows (C2) -> opt-in only
+        bool direct = tb[0] >= lgV && std::getenv("SB_ORBIT_DIRECT") != nullptr;
+        for (int d = 0; d < n; ++d)
+            if (c.dims[d] % ((int64_t)1 << tb[d]) != 0) direct = false;
+        O.direct_store = direct ? 1 : 0;
+        O.st_groups = tile_bytes / (16 * THREADS);
+        auto xbit_off = [&](int p) -> int64_t { // global byte offset of tile-coordinate bit p (output order)
+            for (int d = 0; d < n; ++d)
+                if (p >= xshift[d] && p < xshift[d] + tb[d]) return ((int64_t)1 << (p - xshift[d])) * c.strides[0][d] * esz;
+            return 0;
+        };
+        for (int i = 0; i < LOG_THREADS; ++i) O.st_tcol[i] = xbit_off(i + lgV);
+        for (int r = 0; r < 8; ++r) {
+            int64_t a = 0;
+            for (int i = 0; i < 3; ++i)
+                if ((r >> i) & 1) a += xbit_off(LOG_THREADS + lgV + i);
+            O.st_roff[r] = a;
+        }
+        if (O.st_groups < 1 || O.st_groups > 8) O.direct_store = 0;
+    }
     // guard: the bank model must agree (every warp access of every view is conflict-free)
     for (int v = 0; v <= nin; ++v)
         for (int w = 0; w < THREADS / 32; ++w)
@@ -1058,15 +1130,26 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
                 }
                 if (smem_wavefronts(ea, 32, esz) != (esz == 4 ? 1 : 2)) return false;
             }
-    // ring depth: as many stages as fit beside the two staging buffers (<= 4); small stages leave room for 2 CTAs/SM
-    int ns = (int)((176 * 1024 - 2 * (int64_t)tile_bytes) / O.stage_bytes);
+    // shared memory: `ns` input stages + `ks` output staging buffers.  The TMA unit serves loads and stores in order,
+    // so a store queues behind the prefetch of the next stage: with only two staging buffers the consumers stalled on
+    // it every tile (profiles/r01_v9_orbit_diag.txt: loads and stores each cost 2 us alone, 10 us together).
+    int ks = O.direct_store ? 2 : 4, ns = (int)((208 * 1024 - ks * (int64_t)tile_bytes) / O.stage_bytes);
+    if (ns < 2) {
+        ks = 2;
+        ns = (int)((208 * 1024 - 2 * (int64_t)tile_bytes) / O.stage_bytes);
+    }
     ns = std::max(1, std::min(4, ns));
     if (const char *e = std::getenv("SB_ORBIT_STAGES")) {
         const int v = std::atoi(e);
         if (v >= 1 && v <= 8) ns = v;
     }
+    if (const char *e = std::getenv("SB_ORBIT_STAGING")) {
+        const int v = std::atoi(e);
+        if (v >= 2 && v <= 4 && !O.direct_store) ks = v;
+    }
     O.nstage = ns;
-    plan.orbit_smem_bytes = (int64_t)ns * O.stage_bytes + 2 * (int64_t)tile_bytes + 128;
+    O.nstaging = ks;
+    plan.orbit_smem_bytes = (int64_t)ns * O.stage_bytes + (int64_t)ks * tile_bytes + 128;
     if (plan.orbit_smem_bytes > 224 * 1024) return false;
     Plan::TmaGlobal &gp = plan.orbit_global[0], &go = plan.orbit_global[1];
     gp = Plan::TmaGlobal{};
@@ -1606,7 +1689,7 @@ std::string describe_plan(const Plan &p)
         arr32("tile", P.tile_b, P.ndim);
         if (p.orbit_ok) {
             os << ",\"orbit\":{\"items\":" << p.orbit.nitems << ",\"gmax\":" << p.orbit.gmax << ",\"ept\":" << p.orbit.ept
-               << ",\"nstage\":" << p.orbit.nstage << ",\"tile_bytes\":" << p.orbit.tile_bytes << ",\"smem_bytes\":" << p.orbit_smem_bytes;
+               << ",\"nstage\":" << p.orbit.nstage << ",\"nstaging\":" << p.orbit.nstaging << ",\"direct_store\":" << p.orbit.direct_store << ",\"tile_bytes\":" << p.orbit.tile_bytes << ",\"smem_bytes\":" << p.orbit_smem_bytes;
             arr32("tile", p.orbit_tile_b, P.ndim);
             os << "}";
         }

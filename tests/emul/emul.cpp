@@ -123,7 +123,7 @@ static void emul_box(const Plan::TmaGlobal &g, const int32_t *crd, unsigned char
 template <class CT, int RC, int NIN, int EPT> static void run_orbit(const Plan &plan, int grid)
 {
     const OrbitParams &O = plan.orbit;
-    std::vector<unsigned char> ring((size_t)O.nstage * O.stage_bytes + 2 * (size_t)O.tile_bytes);
+    std::vector<unsigned char> ring((size_t)O.nstage * O.stage_bytes + (size_t)O.nstaging * O.tile_bytes);
     std::vector<OrbitThread<NIN>> th(THREADS);
     for (int t = 0; t < THREADS; ++t) orbit_thread_init<NIN>(O, t, th[t]);
     const uint32_t staging0 = (uint32_t)(O.nstage * O.stage_bytes);
@@ -138,10 +138,15 @@ template <class CT, int RC, int NIN, int EPT> static void run_orbit(const Plan &
             for (int m = 0; m < it.ntile; ++m) {
                 uint32_t slots;
                 std::memcpy(&slots, it.slot[m], 4);
-                const uint32_t sbuf_off = staging0 + (nout & 1u) * (uint32_t)O.tile_bytes;
+                const uint32_t sbuf_off = staging0 + (nout % (uint32_t)O.nstaging) * (uint32_t)O.tile_bytes;
                 for (int t = 0; t < THREADS; ++t)
                     orbit_compute<CT, RC, NIN, EPT>(O, th[t], ring.data(), (uint32_t)(stage * O.stage_bytes), slots, sbuf_off);
-                emul_box(plan.orbit_global[1], it.ocrd[m], plan.map.base[0], ring.data() + sbuf_off, true);
+                if (O.direct_store) {
+                    for (int t = 0; t < THREADS; ++t)
+                        orbit_store_direct(O, t, orbit_store_toff(O, t), ring.data(), sbuf_off, plan.map.base[0] + it.ooff[m]);
+                } else {
+                    emul_box(plan.orbit_global[1], it.ocrd[m], plan.map.base[0], ring.data() + sbuf_off, true);
+                }
                 ++nout;
             }
             if (++stage == O.nstage) stage = 0;

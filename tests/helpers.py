@@ -135,14 +135,16 @@ class Case:
             raise RuntimeError(f"emul_mapreduce failed ({rc}): {lib.emul_last_error().decode()}")
         return bufs[self.views[0].parent]
 
-    def run_gpu(self, mode="device"):
+    def run_gpu(self, mode="device", engine=None):
         import torch
         if mode == "host":
             bufs = self.fresh()
             sb.run_mapreduce(self.tokens, self.op, self.initop, self.init, self.dims, self._svs(bufs))
             return bufs[self.views[0].parent]
         dev = [torch.from_numpy(p.copy()).cuda() for p in self.parents]
-        sb.run_mapreduce(self.tokens, self.op, self.initop, self.init, self.dims, self._svs(dev))
+        if engine is not None:
+            engine.set_stream(torch.cuda.current_stream().cuda_stream)
+        sb.run_mapreduce(self.tokens, self.op, self.initop, self.init, self.dims, self._svs(dev), engine=engine)
         torch.cuda.synchronize()
         return dev[self.views[0].parent].cpu().numpy()
 

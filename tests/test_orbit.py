@@ -10,6 +10,12 @@ import pytest
 from helpers import A, F, K, Case, ViewSpec, SEED, randn, case_c2, case_c4, P_SUM4
 
 
+@pytest.fixture(autouse=True)
+def _two_view_orbits(monkeypatch):
+    """the fused path is the default from three aliased views on; two-view plans (A + A') take it on request"""
+    monkeypatch.setenv("SB_ORBIT_NIN2", "1")
+
+
 def _dense_pair(shape, dt, seed=SEED):
     rng = np.random.default_rng(seed)
     n = int(np.prod(shape))
@@ -92,10 +98,40 @@ def test_orbit_not_chosen_when_output_aliases_parent_or_rows_unaligned():
         assert "orbit" in c.plan(), c.name
 
 
+def test_two_view_plans_default_to_the_tma_ring(monkeypatch):
+    monkeypatch.delenv("SB_ORBIT_NIN2")
+    p = case_c2(4000).plan()
+    assert "orbit" not in p and p["tma"] >= 2
+    assert "orbit" in case_c4(64).plan()
+
+
 _GPU = orbit_cases(big=True)
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case,must", _GPU, ids=[c.name for c, _ in _GPU])
 def test_orbit_gpu(case, must):
-    case.assert_close(case.run_gpu("device"), exact=True)
+    from strided_jl_b200.engine import Engine
+    eng = Engine(0)  # fresh plan cache: the plan is built under this module's environment
+    try:
+        if must:
+            assert "orbit" in case.plan()
+        case.assert_close(case.run_gpu("device", engine=eng), exact=True)
+    finally:
+        eng.close()
+
+
+@pytest.mark.gpu
+def test_orbit_gpu_tma_store_and_direct_store_agree(monkeypatch):
+    """both write-back modes of the fused kernel give the oracle's bytes (C4 has no edge tiles: direct store is legal)"""
+    from strided_jl_b200.engine import Engine
+    for direct in (False, True):
+        if direct:
+            monkeypatch.setenv("SB_ORBIT_DIRECT", "1")
+        for c in (case_c4(32), case_c2(1024)):
+            eng = Engine(0)
+            try:
+                assert c.plan()["orbit"]["direct_store"] == (1 if direct else 0)
+                c.assert_close(c.run_gpu("device", engine=eng), exact=True)
+            finally:
+                eng.close()

@@ -15,44 +15,56 @@ import strided_jl_b200 as sb  # noqa: E402
 from strided_jl_b200.engine import Engine  # noqa: E402
 from tools.profile_case import MAKE  # noqa: E402
 
+N2 = {"SB_ORBIT_NIN2": "1"}
 VARIANTS = {
-    "c2": [{}, {"SB_NO_ORBIT": "1"}, {"SB_ORBIT_BITS": "6"}, {"SB_ORBIT_STAGES": "2"}, {"SB_ORBIT_STAGES": "3"}, {"SB_ORBIT_STAGES": "6"},
-           {"SB_ORBIT_BITS": "6", "SB_ORBIT_STAGES": "1"}],
-    "c4": [{}, {"SB_NO_ORBIT": "1"}, {"SB_ORBIT_STAGES": "1"}, {"SB_ORBIT_STAGES": "3"}],
-    "c4p": [{}, {"SB_NO_ORBIT": "1"}],
+    "c2": [{}, dict(N2), dict(N2, SB_ORBIT_DIRECT="1"), dict(N2, SB_ORBIT_DIRECT="1", SB_ORBIT_BITS="6"),
+           dict(N2, SB_ORBIT_DIRECT="1", SB_ORBIT_BITS="6", SB_DEBUG="nocompute"), dict(N2, SB_ORBIT_BITS="6", SB_DEBUG="nocompute"),
+           dict(N2, SB_ORBIT_STAGES="3"), dict(N2, SB_ORBIT_DIRECT="1", SB_ORBIT_STAGES="3")],
+    "c4": [{}, {"SB_ORBIT_STAGING": "3"}],
+    "c4p": [{}],
     "c1": [{}],
     "c3": [{}],
 }
 
 
 def time_variant(c, dev, env, reps):
+    """us per call, device time: a CUDA graph of `reps` launches replayed (no host launch overhead in the number)"""
     for k in list(os.environ):
         if k.startswith("SB_"):
             del os.environ[k]
     os.environ.update(env)
     eng = Engine(0)
-    eng.set_stream(torch.cuda.current_stream(0).cuda_stream)
     eng.set_sync(False)
     views = c._svs(dev)
-    for _ in range(10):
-        sb.run_mapreduce(c.tokens, c.op, c.initop, c.init, c.dims, views, engine=eng)
-    torch.cuda.synchronize()
+    st = torch.cuda.Stream()
     best = 1e30
-    for _ in range(3):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
+    with torch.cuda.stream(st):
+        eng.set_stream(st.cuda_stream)
+        for _ in range(3):
             sb.run_mapreduce(c.tokens, c.op, c.initop, c.init, c.dims, views, engine=eng)
-        e1.record()
         torch.cuda.synchronize()
-        best = min(best, e0.elapsed_time(e1) * 1e3 / reps)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(reps):
+                sb.run_mapreduce(c.tokens, c.op, c.initop, c.init, c.dims, views, engine=eng)
+        g.replay()
+        torch.cuda.synchronize()
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(5):
+                g.replay()
+            e1.record(st)
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e3 / (5 * reps))
     p = c.plan()
+    del g
     eng.close()
     return best, p
 
 
 def main():
-    reps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+    reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     which = sys.argv[2].split(",") if len(sys.argv) > 2 else list(VARIANTS)
     for nm in which:
         c = MAKE[nm]()
