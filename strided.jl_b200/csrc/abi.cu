@@ -493,7 +493,7 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
         operand_range(desc, plan.base_src[1], lo1, hi1);
         const uintptr_t o0 = (uintptr_t)plan.map.base[0], p0 = (uintptr_t)plan.map.base[1];
         const bool overlap = (o0 + (uintptr_t)lo0 < p0 + (uintptr_t)hi1) && (p0 + (uintptr_t)lo1 < o0 + (uintptr_t)hi0);
-        const OrbitEntry *ok = overlap ? nullptr : find_orbit_kernel(KernelKey{plan.key.ct, plan.key.recipe, plan.orbit.nin, plan.orbit.ept, 1});
+        const OrbitEntry *ok = overlap ? nullptr : find_orbit_kernel(KernelKey{plan.key.ct, plan.key.recipe, plan.orbit.nin, plan.orbit.ept, 1}, plan.orbit.log_threads);
         alignas(64) CUtensorMap maps[2];
         if (ok && encode_orbit_maps(plan, maps)) {
             plan.orbit.out_base = plan.map.base[0];

@@ -234,12 +234,12 @@ SB_HD uint32_t swizzle128(uint32_t d) { return d ^ (((d >> 7) & 7u) << 4); }
 // (nin + 1) x to 2 x the array; the reference gets the same effect from cache blocking inside one task
 // (src/mapreduce.jl:463-500).
 //
-// Thread t handles elements u = t + 256*j of a tile THROUGH A GF(2)-LINEAR MAP x = M u onto the tile's bit-field
+// Thread t of T = 2^log_threads consumers handles elements u = t + T*j of a tile THROUGH A GF(2)-LINEAR MAP x = M u onto the tile's bit-field
 // coordinates, chosen by the planner so that all views' shared-memory reads and the staging write of a warp are
 // bank-conflict free.  Every address functional is again  T(t) XOR J[j].
 constexpr int ORB_MAXG = 4;      // tiles (= parent blocks) per work item
 constexpr int ORB_MAXIN = 4;
-constexpr int ORB_THREADS = THREADS + 32; // 8 consumer warps + 1 producer warp
+constexpr int ORB_MAXLOGT = 9;    // consumer threads: 2^8 (two CTAs per SM possible) or 2^9 (one big CTA per SM), + 1 producer warp
 struct OrbitItem {
     int32_t ntile;
     int32_t pad_;
@@ -250,6 +250,8 @@ struct OrbitItem {
 };
 struct OrbitParams {
     int32_t nin, rank;
+    int32_t log_threads; // log2 of the consumer thread count (8 or 9)
+    int32_t pad0_;
     int32_t nstage;      // depth of the input ring (stages of gmax blocks)
     int32_t tile_bytes;  // one parent block = one output tile
     int32_t stage_bytes; // gmax * tile_bytes
@@ -263,11 +265,11 @@ struct OrbitParams {
     // thread t owning the 16-byte groups g = t + 256 r of the staging buffer; the TMA unit then only serves the loads
     // (it processes box rows at ~2 cycles each, which bounds 32-byte-row tiles when it has to do both directions)
     int32_t direct_store;
-    int32_t st_groups;            // groups per thread per tile = tile_bytes / 4096
+    int32_t st_groups;            // groups per thread per tile = tile_bytes / (16 * consumer threads)
     unsigned char *out_base;
-    int64_t st_tcol[LOG_THREADS]; // global byte offset contributed by bit i of t
+    int64_t st_tcol[ORB_MAXLOGT]; // global byte offset contributed by bit i of t
     int64_t st_roff[8];           // ... by r
-    uint32_t tcol[ORB_MAXIN + 1][LOG_THREADS]; // byte-address image of thread bit i; view 0 = output staging, k = input k
+    uint32_t tcol[ORB_MAXIN + 1][ORB_MAXLOGT]; // byte-address image of thread bit i; view 0 = output staging, k = input k
     uint32_t jtab[ORB_MAXIN + 1][MAXEPT];      // byte-address image of j
     Program prog;
 };

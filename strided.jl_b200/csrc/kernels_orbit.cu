@@ -1,7 +1,9 @@
 // kernels_orbit.cu -- instantiations of the alias-fused ("orbit") map kernel.  Mirrored by planner.cpp: orbit_instantiated().
 #include "orbit_kernel.cuh"
 namespace sb {
-#define SB_ORBIT_EPTS(CT, DT, RC, NIN) SB_ORBIT_ENTRY(CT, DT, RC, NIN, 4), SB_ORBIT_ENTRY(CT, DT, RC, NIN, 8), SB_ORBIT_ENTRY(CT, DT, RC, NIN, 16)
+#define SB_ORBIT_EPTS(CT, DT, RC, NIN)                                                                               \
+    SB_ORBIT_ENTRY(CT, DT, RC, NIN, 4, 8), SB_ORBIT_ENTRY(CT, DT, RC, NIN, 8, 8), SB_ORBIT_ENTRY(CT, DT, RC, NIN, 16, 8),  \
+        SB_ORBIT_ENTRY(CT, DT, RC, NIN, 2, 9), SB_ORBIT_ENTRY(CT, DT, RC, NIN, 4, 9), SB_ORBIT_ENTRY(CT, DT, RC, NIN, 8, 9)
 #define SB_ORBIT_TYPE(CT, DT)                                                                                        \
     SB_ORBIT_EPTS(CT, DT, RC_ADD2, 2), SB_ORBIT_EPTS(CT, DT, RC_ADD2_MUL, 2), SB_ORBIT_EPTS(CT, DT, RC_ADD2_DIV, 2),   \
         SB_ORBIT_EPTS(CT, DT, RC_AXPY, 2), SB_ORBIT_EPTS(CT, DT, RC_AXPBY, 2), SB_ORBIT_EPTS(CT, DT, RC_SUM3, 3),      \
@@ -12,13 +14,13 @@ const OrbitEntry *orbit_table(int *n)
     *n = (int)(sizeof(tab) / sizeof(tab[0]));
     return tab;
 }
-const OrbitEntry *find_orbit_kernel(const KernelKey &k)
+const OrbitEntry *find_orbit_kernel(const KernelKey &k, int logt)
 {
     int n = 0;
     const OrbitEntry *t = orbit_table(&n);
     for (int i = 0; i < n; ++i) {
         const KernelKey &e = t[i].key;
-        if (e.ct == k.ct && e.recipe == k.recipe && e.nin == k.nin && e.ept == k.ept) return &t[i];
+        if (e.ct == k.ct && e.recipe == k.recipe && e.nin == k.nin && e.ept == k.ept && t[i].logt == logt) return &t[i];
     }
     return nullptr;
 }

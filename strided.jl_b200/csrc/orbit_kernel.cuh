@@ -64,8 +64,8 @@ __device__ __forceinline__ void tma_store_rank(int rank, const CUtensorMap *map,
 
 constexpr int ORB_MAXSTAGE = 8;
 
-template <class CT, int RC, int NIN, int EPT>
-__global__ void __launch_bounds__(ORB_THREADS, 2)
+template <class CT, int RC, int NIN, int EPT, int LOGT>
+__global__ void __launch_bounds__((1 << LOGT) + 32, LOGT == 8 ? 2 : 1)
 map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ CUtensorMap min, const __grid_constant__ CUtensorMap mout)
 {
     extern __shared__ unsigned char sb_orbit_smem_raw[];
@@ -75,12 +75,13 @@ map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ 
     // ring (nstage stages of gmax blocks) followed by two staging buffers; TMA needs 128-byte aligned boxes
     unsigned char *ring = sb_orbit_smem_raw + ((0u - smem_u32(sb_orbit_smem_raw)) & 127u); // (offset form keeps the address space known: LDS/STS)
     const uint32_t ring_u32 = smem_u32(ring);
+    constexpr int NT = 1 << LOGT; // consumer threads
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = O.nstage;
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
-            mbar_init(smem_u32(&empty_bar[s]), THREADS / 32);
+            mbar_init(smem_u32(&empty_bar[s]), NT / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -89,7 +90,7 @@ map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ 
     const uint32_t grid = gridDim.x;
     constexpr int IW = (int)(sizeof(OrbitItem) / 4); // words per work item
     static_assert(sizeof(OrbitItem) % 4 == 0 && IW <= 64, "OrbitItem is copied as <= 2 words per producer lane");
-    if (warp == THREADS / 32) {
+    if (warp == NT / 32) {
         // ---------------- producer warp ----------------
         // The work item (coordinates, slots) travels with the stage: the producer copies it into shared memory before
         // arming the full barrier, so that no consumer ever waits on a dependent global load (measured: the item loads
@@ -151,7 +152,7 @@ map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ 
                 if (O.direct_store) {
                     // two staging buffers: a thread can only reach the writes of tile m+2 (same buffer) through the barrier
                     // of tile m+1, which every thread passes after its own reads of tile m below
-                    if (!(O.debug & 16)) asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+                    if (!(O.debug & 16)) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
                     if (!(O.debug & 2)) orbit_store_direct(O, tid, st_t, ring, sbuf_off, O.out_base + it->ooff[m]);
                 } else {
                     if (!(O.debug & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the TMA store
@@ -164,7 +165,7 @@ map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ 
                         default: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
                         }
                     }
-                    if (!(O.debug & 16)) asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+                    if (!(O.debug & 16)) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
                     if (tid == 0 && !(O.debug & 2)) {
                         tma_store_rank(O.rank, &mout, ring_u32 + sbuf_off, it->ocrd[m]);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -185,35 +186,36 @@ map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ 
 
 struct OrbitEntry {
     KernelKey key;
+    int logt;
     cudaError_t (*launch)(const OrbitParams &, const CUtensorMap *, int grid, size_t smem, cudaStream_t);
     cudaError_t (*occupancy)(int *nblocks, size_t smem);
     const void *func;
 };
 
-template <class CT, int RC, int NIN, int EPT> struct OrbitLaunch {
+template <class CT, int RC, int NIN, int EPT, int LOGT> struct OrbitLaunch {
     static cudaError_t launch(const OrbitParams &O, const CUtensorMap *maps, int grid, size_t smem, cudaStream_t s)
     {
-        auto k = map_orbit_kernel<CT, RC, NIN, EPT>;
+        auto k = map_orbit_kernel<CT, RC, NIN, EPT, LOGT>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        k<<<grid, ORB_THREADS, smem, s>>>(O, maps[0], maps[1]);
+        k<<<grid, (1 << LOGT) + 32, smem, s>>>(O, maps[0], maps[1]);
         return cudaGetLastError();
     }
     static cudaError_t occupancy(int *nb, size_t smem)
     {
-        auto k = map_orbit_kernel<CT, RC, NIN, EPT>;
+        auto k = map_orbit_kernel<CT, RC, NIN, EPT, LOGT>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, ORB_THREADS, smem);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, (1 << LOGT) + 32, smem);
     }
-    static const void *func() { return (const void *)map_orbit_kernel<CT, RC, NIN, EPT>; }
+    static const void *func() { return (const void *)map_orbit_kernel<CT, RC, NIN, EPT, LOGT>; }
 };
 
-#define SB_ORBIT_ENTRY(CT, DT, RC, NIN, EPT)                                                                         \
-    OrbitEntry { KernelKey{DT, RC, NIN, EPT, 1}, &OrbitLaunch<CT, RC, NIN, EPT>::launch, &OrbitLaunch<CT, RC, NIN, EPT>::occupancy, \
-                 OrbitLaunch<CT, RC, NIN, EPT>::func() }
+#define SB_ORBIT_ENTRY(CT, DT, RC, NIN, EPT, LOGT)                                                                   \
+    OrbitEntry { KernelKey{DT, RC, NIN, EPT, 1}, LOGT, &OrbitLaunch<CT, RC, NIN, EPT, LOGT>::launch,                 \
+                 &OrbitLaunch<CT, RC, NIN, EPT, LOGT>::occupancy, OrbitLaunch<CT, RC, NIN, EPT, LOGT>::func() }
 
 const OrbitEntry *orbit_table(int *n);
-const OrbitEntry *find_orbit_kernel(const KernelKey &k);
+const OrbitEntry *find_orbit_kernel(const KernelKey &k, int logt);
 
 } // namespace sb

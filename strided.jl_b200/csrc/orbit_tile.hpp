@@ -23,8 +23,8 @@ template <int NIN> SB_HD void orbit_thread_init(const OrbitParams &O, int t, Orb
     for (int k = 0; k <= NIN; ++k) {
         uint32_t a = 0;
 #pragma unroll
-        for (int i = 0; i < LOG_THREADS; ++i)
-            if ((t >> i) & 1) a ^= O.tcol[k][i];
+        for (int i = 0; i < ORB_MAXLOGT; ++i)
+            if (i < O.log_threads && ((t >> i) & 1)) a ^= O.tcol[k][i];
         th.T[k] = a;
     }
 }
@@ -69,8 +69,8 @@ SB_HD int64_t orbit_store_toff(const OrbitParams &O, int t)
 {
     int64_t a = 0;
 #pragma unroll
-    for (int i = 0; i < LOG_THREADS; ++i)
-        if ((t >> i) & 1) a += O.st_tcol[i];
+    for (int i = 0; i < ORB_MAXLOGT; ++i)
+        if (i < O.log_threads && ((t >> i) & 1)) a += O.st_tcol[i];
     return a;
 }
 SB_HD void orbit_store_direct(const OrbitParams &O, int t, int64_t st_t, const unsigned char *ring, uint32_t sbuf_off, unsigned char *out_tile)
@@ -80,10 +80,10 @@ SB_HD void orbit_store_direct(const OrbitParams &O, int t, int64_t st_t, const u
 #pragma unroll 4
     for (int r = 0; r < O.st_groups; ++r) {
 #if defined(__CUDA_ARCH__)
-        const OrbitVec16 v = *reinterpret_cast<const OrbitVec16 *>(src + (size_t)r * (16u * THREADS));
+        const OrbitVec16 v = *reinterpret_cast<const OrbitVec16 *>(src + (size_t)r * (16u << O.log_threads));
         __stcs(reinterpret_cast<uint4 *>(dst + O.st_roff[r]), make_uint4(v.w[0], v.w[1], v.w[2], v.w[3])); // streaming: never re-read
 #else
-        for (int b = 0; b < 16; ++b) dst[O.st_roff[r] + b] = src[(size_t)r * (16u * THREADS) + b]; // (host emulation: no alignment assumed)
+        for (int b = 0; b < 16; ++b) dst[O.st_roff[r] + b] = src[(size_t)r * (16u << O.log_threads) + b]; // (host emulation: no alignment assumed)
 #endif
     }
 }

@@ -758,10 +758,10 @@ bool plan_tma(const Canon &c, const MapParams &P, const int *tdim, Plan &plan)
 
 // ---- alias-fused ("orbit") variant ---------------------------------------------------------------------------
 // mirrored by csrc/kernels_orbit.cu
-bool orbit_instantiated(int ct, int recipe, int nin, int ept)
+bool orbit_instantiated(int ct, int recipe, int nin, int ept, int logt)
 {
     if (ct != F32 && ct != F64) return false;
-    if (ept != 4 && ept != 8 && ept != 16) return false;
+    if (logt == 8 ? (ept != 4 && ept != 8 && ept != 16) : (logt != 9 || (ept != 2 && ept != 4 && ept != 8))) return false;
     switch (recipe) {
     case RC_ADD2: case RC_ADD2_MUL: case RC_ADD2_DIV: case RC_AXPY: case RC_AXPBY: return nin == 2;
     case RC_SUM3: return nin == 3;
@@ -887,9 +887,18 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
         }
     }
     if (!found) return false;
-    const int ept = 1 << (ebits - LOG_THREADS);
-    if (!orbit_instantiated(c.ct, prog.recipe, nin, ept)) return false;
     const int32_t tile_bytes = esz << ebits;
+    // consumer threads: 256.  512 (16 warps) are instantiated too but measure the same (config 4: 30.0 vs 29.7 us,
+    // profiles/r01_v9_orbit_threads_lpt.txt): the tile loop is bound by shared-memory bandwidth and by the SM's memory
+    // request rate (32-byte box rows), not by latency.
+    int logt = 8;
+    if (const char *e = std::getenv("SB_ORBIT_LOGT")) {
+        const int v = std::atoi(e);
+        if ((v == 8 || v == 9) && ebits - v >= 1) logt = v;
+    }
+    const int ept = 1 << (ebits - logt);
+    if (!orbit_instantiated(c.ct, prog.recipe, nin, ept, logt)) return false;
+    const int nthreads = 1 << logt;
 
     // ---- work items: orbits of the tile grid under  c -> pb_1^-1(pb_k(c)) --------------------------------------
     int64_t ntile[MAXD], ntiles = 1;
@@ -1000,6 +1009,11 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
         items.push_back(it);
     }
 
+    // Longest items first: the short orbits (tiles on a diagonal of the tile grid: fewer distinct images) go to the END of
+    // the launch order, so that the CTAs that get one item more than the others in the last round get a short one
+    // (config 4: 1044 items on 148 CTAs = 7 rounds + 8 items; those 8 are now 1- and 2-tile orbits).
+    std::stable_partition(items.begin(), items.end(), [&](const OrbitItem &it) { return it.ntile == gmax; });
+
     // ---- thread map x = M u over GF(2): conflict-free shared-memory access for every view ----------------------
     const int B = ebits, lg = esz == 4 ? 2 : 3;
     const int L = esz == 4 ? 5 : 4; // lanes served together: a warp of 4-byte or a half-warp of 8-byte accesses
@@ -1068,6 +1082,7 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
     O.gmax = gmax;
     O.stage_bytes = gmax * tile_bytes;
     O.ept = ept;
+    O.log_threads = logt;
     O.nitems = (int32_t)items.size();
     O.prog = prog;
     if (const char *dbg = std::getenv("SB_DEBUG")) { // diagnostics only: results are WRONG with these
@@ -1084,11 +1099,11 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
         return a;
     };
     for (int v = 0; v <= nin; ++v) {
-        for (int i = 0; i < LOG_THREADS; ++i) O.tcol[v][i] = addr_image(v, col[i]);
+        for (int i = 0; i < logt; ++i) O.tcol[v][i] = addr_image(v, col[i]);
         for (int j = 0; j < ept; ++j) {
             uint32_t a = 0;
-            for (int i = 0; i + LOG_THREADS < B; ++i)
-                if ((j >> i) & 1) a ^= addr_image(v, col[LOG_THREADS + i]);
+            for (int i = 0; i + logt < B; ++i)
+                if ((j >> i) & 1) a ^= addr_image(v, col[logt + i]);
             O.jtab[v][j] = a;
         }
     }
@@ -1101,30 +1116,30 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
         for (int d = 0; d < n; ++d)
             if (c.dims[d] % ((int64_t)1 << tb[d]) != 0) direct = false;
         O.direct_store = direct ? 1 : 0;
-        O.st_groups = tile_bytes / (16 * THREADS);
+        O.st_groups = tile_bytes / (16 * nthreads);
         auto xbit_off = [&](int p) -> int64_t { // global byte offset of tile-coordinate bit p (output order)
             for (int d = 0; d < n; ++d)
                 if (p >= xshift[d] && p < xshift[d] + tb[d]) return ((int64_t)1 << (p - xshift[d])) * c.strides[0][d] * esz;
             return 0;
         };
-        for (int i = 0; i < LOG_THREADS; ++i) O.st_tcol[i] = xbit_off(i + lgV);
+        for (int i = 0; i < logt; ++i) O.st_tcol[i] = xbit_off(i + lgV);
         for (int r = 0; r < 8; ++r) {
             int64_t a = 0;
             for (int i = 0; i < 3; ++i)
-                if ((r >> i) & 1) a += xbit_off(LOG_THREADS + lgV + i);
+                if ((r >> i) & 1) a += xbit_off(logt + lgV + i);
             O.st_roff[r] = a;
         }
         if (O.st_groups < 1 || O.st_groups > 8) O.direct_store = 0;
     }
     // guard: the bank model must agree (every warp access of every view is conflict-free)
     for (int v = 0; v <= nin; ++v)
-        for (int w = 0; w < THREADS / 32; ++w)
+        for (int w = 0; w < nthreads / 32; ++w)
             for (int j = 0; j < ept; ++j) {
                 int32_t ea[32];
                 for (int l = 0; l < 32; ++l) {
                     uint32_t a = O.jtab[v][j];
                     const int t = w * 32 + l;
-                    for (int i = 0; i < LOG_THREADS; ++i)
+                    for (int i = 0; i < logt; ++i)
                         if ((t >> i) & 1) a ^= O.tcol[v][i];
                     ea[l] = (int32_t)(a >> lg);
                 }
@@ -1688,7 +1703,7 @@ std::string describe_plan(const Plan &p)
         arr64("dims", P.dims, P.ndim);
         arr32("tile", P.tile_b, P.ndim);
         if (p.orbit_ok) {
-            os << ",\"orbit\":{\"items\":" << p.orbit.nitems << ",\"gmax\":" << p.orbit.gmax << ",\"ept\":" << p.orbit.ept
+            os << ",\"orbit\":{\"items\":" << p.orbit.nitems << ",\"gmax\":" << p.orbit.gmax << ",\"ept\":" << p.orbit.ept << ",\"threads\":" << (1 << p.orbit.log_threads)
                << ",\"nstage\":" << p.orbit.nstage << ",\"nstaging\":" << p.orbit.nstaging << ",\"direct_store\":" << p.orbit.direct_store << ",\"tile_bytes\":" << p.orbit.tile_bytes << ",\"smem_bytes\":" << p.orbit_smem_bytes;
             arr32("tile", p.orbit_tile_b, P.ndim);
             os << "}";

@@ -124,8 +124,9 @@ template <class CT, int RC, int NIN, int EPT> static void run_orbit(const Plan &
 {
     const OrbitParams &O = plan.orbit;
     std::vector<unsigned char> ring((size_t)O.nstage * O.stage_bytes + (size_t)O.nstaging * O.tile_bytes);
-    std::vector<OrbitThread<NIN>> th(THREADS);
-    for (int t = 0; t < THREADS; ++t) orbit_thread_init<NIN>(O, t, th[t]);
+    const int NT = 1 << O.log_threads;
+    std::vector<OrbitThread<NIN>> th(NT);
+    for (int t = 0; t < NT; ++t) orbit_thread_init<NIN>(O, t, th[t]);
     const uint32_t staging0 = (uint32_t)(O.nstage * O.stage_bytes);
     for (int b = 0; b < grid; ++b) {
         int stage = 0;
@@ -139,10 +140,10 @@ template <class CT, int RC, int NIN, int EPT> static void run_orbit(const Plan &
                 uint32_t slots;
                 std::memcpy(&slots, it.slot[m], 4);
                 const uint32_t sbuf_off = staging0 + (nout % (uint32_t)O.nstaging) * (uint32_t)O.tile_bytes;
-                for (int t = 0; t < THREADS; ++t)
+                for (int t = 0; t < NT; ++t)
                     orbit_compute<CT, RC, NIN, EPT>(O, th[t], ring.data(), (uint32_t)(stage * O.stage_bytes), slots, sbuf_off);
                 if (O.direct_store) {
-                    for (int t = 0; t < THREADS; ++t)
+                    for (int t = 0; t < NT; ++t)
                         orbit_store_direct(O, t, orbit_store_toff(O, t), ring.data(), sbuf_off, plan.map.base[0] + it.ooff[m]);
                 } else {
                     emul_box(plan.orbit_global[1], it.ocrd[m], plan.map.base[0], ring.data() + sbuf_off, true);
@@ -159,6 +160,7 @@ template <class CT> static bool orbit_dispatch(const Plan &plan, int grid)
     const int rc = plan.key.recipe, nin = plan.orbit.nin, ept = plan.orbit.ept;
 #define TRYO(R, N)                                                                                                   \
     if (rc == R && nin == N) {                                                                                       \
+        if (ept == 2) { run_orbit<CT, R, N, 2>(plan, grid); return true; }                                           \
         if (ept == 4) { run_orbit<CT, R, N, 4>(plan, grid); return true; }                                           \
         if (ept == 8) { run_orbit<CT, R, N, 8>(plan, grid); return true; }                                           \
         if (ept == 16) { run_orbit<CT, R, N, 16>(plan, grid); return true; }                                         \

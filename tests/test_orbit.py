@@ -77,10 +77,19 @@ def test_orbit_emulated(case, must):
     if must:
         assert "orbit" in plan, plan
         o = plan["orbit"]
-        assert o["ept"] in (4, 8, 16) and o["gmax"] <= 4 and o["smem_bytes"] <= 224 * 1024
+        assert o["ept"] * o["threads"] in (1024, 2048, 4096) and o["gmax"] <= 4 and o["smem_bytes"] <= 224 * 1024
     want = case.expected()
     case.assert_close(case.run_emul(), want, exact=True)
     case.assert_close(case.run_emul(grid_limit=2), want, exact=True)  # few persistent CTAs: ring wrap-around, staging parity
+
+
+@pytest.mark.parametrize("logt", ["8", "9"])
+def test_orbit_emulated_both_thread_counts(monkeypatch, logt):
+    monkeypatch.setenv("SB_ORBIT_LOGT", logt)
+    for c in (case_c4(16), case_c4(16, np.float64), case_c2(256), case_c2(128, np.float32)):
+        assert c.plan()["orbit"]["threads"] == 1 << int(logt), c.name
+        c.assert_close(c.run_emul(), exact=True)
+        c.assert_close(c.run_emul(grid_limit=1), exact=True)
 
 
 def test_orbit_not_chosen_when_output_aliases_parent_or_rows_unaligned():

@@ -17,11 +17,12 @@ from tools.profile_case import MAKE  # noqa: E402
 
 N2 = {"SB_ORBIT_NIN2": "1"}
 VARIANTS = {
-    "c2": [{}, dict(N2), dict(N2, SB_ORBIT_DIRECT="1"), dict(N2, SB_ORBIT_DIRECT="1", SB_ORBIT_BITS="6"),
-           dict(N2, SB_ORBIT_DIRECT="1", SB_ORBIT_BITS="6", SB_DEBUG="nocompute"), dict(N2, SB_ORBIT_BITS="6", SB_DEBUG="nocompute"),
-           dict(N2, SB_ORBIT_STAGES="3"), dict(N2, SB_ORBIT_DIRECT="1", SB_ORBIT_STAGES="3")],
-    "c4": [{}, {"SB_ORBIT_STAGING": "3"}],
-    "c4p": [{}],
+    "c2": [{}, dict(N2), dict(N2, SB_ORBIT_STAGES="3")],
+    "c4": [{}, {"SB_ORBIT_LOGT": "8"}, {"SB_ORBIT_STAGING": "3"}, {"SB_ORBIT_SUPER": "0"}, {"SB_ORBIT_SUPER": "1"}, {"SB_ORBIT_SUPER": "3"},
+           {"SB_ORBIT_LOGT": "8", "SB_ORBIT_STAGES": "1", "SB_ORBIT_STAGING": "2"},
+           {"SB_DEBUG": "noload,nostore"}, {"SB_ORBIT_LOGT": "8", "SB_DEBUG": "noload,nostore"}, {"SB_DEBUG": "nocompute"},
+           {"SB_DEBUG": "noload,nostore,nocompute"}],
+    "c4p": [{}, {"SB_ORBIT_LOGT": "8"}],
     "c1": [{}],
     "c3": [{}],
 }
