@@ -15,7 +15,7 @@ from .broadcast import (Broadcasted, Ref, Arg, materialize, materialize_, captur
                         tanh, inv, add, sub, mul, div, maximum2, minimum2, lt)
 from .engine import get_engine, make_desc, run_mapreduce, similar_parent
 from .mapreduce import (map_, map, copy_, conj_, adjoint_, transpose_, permutedims_, mapreduce, mapreducedim_,
-                        _mapreducedim_, sum, prod, maximum, minimum, rmul_, lmul_, mul_, axpy_, axpby_)
+                        _mapreducedim_, sum, prod, maximum, minimum, rmul_, lmul_, mul_, axpy_, axpby_, mul_generic_, _mul_generic_call)
 
 from . import sharded
 from .sharded import sharded_mapreduce, sharded_map_, shard_view, shard_range

@@ -80,8 +80,8 @@ map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ 
     const int S = O.nstage;
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(smem_u32(&full_bar[s]), 1);
-            mbar_init(smem_u32(&empty_bar[s]), NT / 32);
+            mbar_init(smem_u32(&full_bar[s]), 32); // every producer lane arrives: each releases its own item words
+            mbar_init(smem_u32(&empty_bar[s]), NT);  // every consumer thread arrives after its last read of the stage
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -120,7 +120,8 @@ map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ 
             const OrbitItem *it = reinterpret_cast<const OrbitItem *>(d);
             const int ntile = it->ntile;
             const uint32_t fb = smem_u32(&full_bar[stage]);
-            if (lane == 0) mbar_expect_tx(fb, (uint32_t)(ntile * O.tile_bytes)); // (release: the item words above are visible)
+            if (lane == 0) mbar_expect_tx(fb, (uint32_t)(ntile * O.tile_bytes)); // arrive (release) + transaction bytes
+            else mbar_arrive(fb);                                                // arrive (release) of this lane's item words
             __syncwarp();
             if (O.debug & 1) {
                 if (lane == 0) asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(fb), "r"((uint32_t)(ntile * O.tile_bytes)) : "memory");
@@ -173,8 +174,7 @@ map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ 
                 }
                 if (++sbuf == (uint32_t)K) sbuf = 0;
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage])); // this warp is done with the stage (and its item copy)
+            mbar_arrive(smem_u32(&empty_bar[stage])); // this thread is done with the stage (and its item copy)
             if (++stage == S) {
                 stage = 0;
                 parity ^= 1u;

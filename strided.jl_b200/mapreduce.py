@@ -226,3 +226,35 @@ def axpby_(a, X, b, Y):
     """Y .= a .* X .+ b .* Y   (linalg.jl:32-42)."""
     X, Y = maybestrided(X), maybestrided(Y)
     return materialize_(Y, Broadcasted("add", (Broadcasted("mul", (a, X)), Broadcasted("mul", (b, Y)))))
+
+
+# ---- generic matrix multiplication as a 3-D map-reduce  (linalg.jl:44-49, 130-162) ---------------------------
+def _mul_generic_call(C, A, B, alpha=1, beta=0):
+    """The `_mapreducedim!` call `__mul!(C, A, B, α, β)` makes (linalg.jl:130-162):  C2 = sreshape(C, (m,n,1)),
+    A2 = sreshape(A, (m,1,k)), B2 = sreshape(permutedims(B,(2,1)), (1,n,k)), f = * or (x,y)->x*y*α, op = +,
+    initop = zero | nothing | x->x*β.  Returns None when the reference short-cuts to `rmul!(C, β)` (α == 0 or k == 0),
+    else (f, op, initop, dims, arrays)."""
+    C, A, B = maybestrided(C), maybestrided(A), maybestrided(B)
+    if not (C.ndim == A.ndim == B.ndim == 2 and C.size[0] == A.size[0] and C.size[1] == B.size[1] and A.size[1] == B.size[0]):
+        raise DimensionMismatchError(f"A has size {A.size}, B has size {B.size}, C has size {C.size}")  # linalg.jl:132-133
+    (m, n), k = C.size, A.size[1]
+    if alpha == 0 or k == 0:
+        return None
+    A2 = A.sreshape((m, 1, k))
+    B2 = B.permutedims((1, 0)).sreshape((1, n, k))
+    C2 = C.sreshape((m, n, 1))
+    f = "mul" if alpha == 1 else (lambda x, y: x * y * alpha)
+    initop = "zero" if beta == 0 else (None if beta == 1 else ("scale", beta))
+    return f, "+", initop, (m, n, k), (C2, A2, B2)
+
+
+def mul_generic_(C, A, B, alpha=1, beta=0):
+    """`mul!(C, A, B, α, β)` through the generic path `__mul!` (linalg.jl:44-49, 130-162): one fused
+    initop + map + reduce launch, no temporaries.  (For BLAS eltypes the reference dispatches to `gemm!`,
+    linalg.jl:50-127 -- a dense contraction, out of this engine's scope: call cuBLAS for that.)"""
+    call = _mul_generic_call(C, A, B, alpha, beta)
+    if call is None:
+        return rmul_(C, beta)
+    f, op, initop, dims, arrays = call
+    _mapreducedim_(f, op, initop, dims, arrays)
+    return maybestrided(C)
