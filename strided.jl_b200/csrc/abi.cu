@@ -348,6 +348,22 @@ static int occupancy_of(sb_ctx *ctx, const void *func, cudaError_t (*occ)(int *,
     return SB_OK;
 }
 
+// launch of a run-time compiled kernel (same bodies, same PDL contract as the static ones)
+static cudaError_t launch_jit(const void *fn, unsigned grid, size_t smem, cudaStream_t s, void **args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelExC(&cfg, fn, args);
+}
+
 static int run_desc(sb_ctx *ctx, const sb_desc &desc)
 {
     // plan cache: everything but the base pointers (the reference re-plans on every call; config 3 is ~2 us
@@ -449,7 +465,9 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
     // Run-time specialised element function (NVRTC) instead of the interpreter, once the problem is large enough to
     // amortise a ~2 s compile (the GPU analog of MINTHREADLENGTH, reference src/mapreduce.jl:141).
     const JitKernel *jk = nullptr;
-    if (plan.key.recipe == RC_INTERP && jit_enabled()) {
+    // (plans with an alias-fused orbit variant keep the in-kernel interpreter: the orbit kernel is bound by its memory
+    //  request rate, not by instruction issue, and beats the generic kernel + JIT by 2-3x on aliased views)
+    if (plan.key.recipe == RC_INTERP && jit_enabled() && !(plan.kind == PLAN_MAP && plan.orbit_ok)) {
         static const int64_t jit_min = []() {
             const char *e = std::getenv("SB_JIT_MIN_ELEMENTS");
             return e ? (int64_t)std::atoll(e) : ((int64_t)1 << 20);
@@ -479,7 +497,7 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
             int64_t grid = std::min<int64_t>(plan.map.ntiles, (int64_t)ctx->dev.sm_count * nb);
             if (grid < 1) grid = 1;
             void *args[] = {(void *)&plan.map};
-            cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(THREADS), args, (size_t)plan.smem_bytes, ctx->stream);
+            cudaError_t e = launch_jit(fn, (unsigned)grid, (size_t)plan.smem_bytes, ctx->stream, args);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "jit map launch");
             ctx->stats.launches++;
             ctx->stats.jit_launches++;
@@ -561,7 +579,7 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
         cudaError_t e;
         if (jk) {
             void *args[] = {(void *)&plan.red};
-            e = cudaLaunchKernel((const void *)jk->fn, dim3((unsigned)plan.grid), dim3(THREADS), args, (size_t)plan.smem_bytes, ctx->stream);
+            e = launch_jit((const void *)jk->fn, (unsigned)plan.grid, (size_t)plan.smem_bytes, ctx->stream, args);
         } else {
             e = k->launch(plan.red, (int)plan.grid, (size_t)plan.smem_bytes, ctx->stream);
         }

@@ -36,6 +36,21 @@ using cuda::std::uintptr_t;
 
 namespace sb {
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// Every kernel of this library is launched with programmaticStreamSerializationAllowed: in a sequence of calls (what a
+// Julia program issuing one `@strided` statement after another produces) the NEXT kernel's launch latency and prologue
+// (parameter loads, mbarrier init, per-thread offset functionals) overlap the tail of the previous one.  Correctness:
+// every kernel executes griddepcontrol.wait -- which returns only when the preceding grid has completed and its
+// memory is visible -- before its first access to global memory that a previous kernel may have written or read.
+// (Both instructions are no-ops for a kernel that was not launched programmatically.)
+#if defined(__CUDA_ARCH__)
+SB_D void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+SB_D void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#else
+SB_D void pdl_launch_dependents() {}
+SB_D void pdl_wait() {}
+#endif
+
 constexpr int MAXD = 8;    // SB_MAX_DIMS
 constexpr int MAXO = 8;    // SB_MAX_OPS (operand 0 = output)
 constexpr int MAXIN = MAXO - 1;

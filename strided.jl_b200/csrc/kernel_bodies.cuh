@@ -20,9 +20,11 @@ template <class CT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forcein
 {
     extern __shared__ __align__(16) unsigned char sb_smem_raw[];
     const int t = threadIdx.x;
+    pdl_launch_dependents();
     MapThread<NIN + 1> th;
     map_thread_init<NIN + 1>(P, t, th);
     const bool staged = P.nstaged > 0;
+    pdl_wait(); // first global access below
     const uint32_t ntiles = (uint32_t)P.ntiles;
     for (uint32_t pos = blockIdx.x; pos < ntiles; pos += gridDim.x) {
         MapTile<NIN + 1> tl;
@@ -55,6 +57,8 @@ template <class AT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forcein
     AT *smem = reinterpret_cast<AT *>(sb_smem_raw);
     const int t = threadIdx.x;
     const uint32_t bid = blockIdx.x;
+    pdl_launch_dependents();
+    pdl_wait(); // (the previous launch may be a reduction re-arming the same arrival counters)
     red_accumulate<AT, RC, NIN, EPT, UNIFORM>(P, bid, t, smem);
     __syncthreads();
     if (P.warp_per_output) {
@@ -97,6 +101,7 @@ template <class AT, bool UNIFORM> __device__ __forceinline__ void reduce_finaliz
 {
     const int64_t out_idx = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    pdl_wait();
     if (out_idx >= P.nouttiles * (int64_t)P.nout_tile) return; // warp-uniform
     AT p = red_finalize_lane<AT>(P, out_idx, lane);
 #pragma unroll

@@ -3,8 +3,28 @@
 #include "kernel_bodies.cuh"
 #include "planner.hpp"
 #include <cuda_runtime.h>
+#include <cstdlib>
+#include <utility>
 
 namespace sb {
+
+// launch with programmatic stream serialisation (see common.hpp "PDL"); SB_NO_PDL=1 turns the attribute off
+inline bool pdl_enabled() { return std::getenv("SB_NO_PDL") == nullptr; } // (re-read per launch: tools toggle it at run time)
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*k)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k, std::forward<Args>(args)...);
+}
 
 // ---- statically instantiated kernels (the bodies live in kernel_bodies.cuh) ------------------------------------
 template <class CT, int RC, int NIN, int EPT, bool UNIFORM>
@@ -45,8 +65,7 @@ template <class CT, int RC, int NIN, int EPT, bool U> struct MapLaunch {
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        k<<<grid, THREADS, smem, s>>>(P);
-        return cudaGetLastError();
+        return launch_pdl(k, grid, THREADS, smem, s, P);
     }
     static cudaError_t occupancy(int *nb, size_t smem)
     {
@@ -68,13 +87,11 @@ template <class AT, int RC, int NIN, int EPT, bool U> struct ReduceLaunch {
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        k<<<grid, THREADS, smem, s>>>(P);
-        return cudaGetLastError();
+        return launch_pdl(k, grid, THREADS, smem, s, P);
     }
     static cudaError_t finalize(const ReduceParams &P, int grid, cudaStream_t s)
     {
-        reduce_finalize_kernel<AT, U><<<grid, THREADS, 0, s>>>(P);
-        return cudaGetLastError();
+        return launch_pdl(reduce_finalize_kernel<AT, U>, grid, THREADS, 0, s, P);
     }
     static cudaError_t occupancy(int *nb, size_t smem)
     {

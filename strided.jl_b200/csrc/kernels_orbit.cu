@@ -7,7 +7,8 @@ namespace sb {
 #define SB_ORBIT_TYPE(CT, DT)                                                                                        \
     SB_ORBIT_EPTS(CT, DT, RC_ADD2, 2), SB_ORBIT_EPTS(CT, DT, RC_ADD2_MUL, 2), SB_ORBIT_EPTS(CT, DT, RC_ADD2_DIV, 2),   \
         SB_ORBIT_EPTS(CT, DT, RC_AXPY, 2), SB_ORBIT_EPTS(CT, DT, RC_AXPBY, 2), SB_ORBIT_EPTS(CT, DT, RC_SUM3, 3),      \
-        SB_ORBIT_EPTS(CT, DT, RC_SUM4, 4)
+        SB_ORBIT_EPTS(CT, DT, RC_SUM4, 4), SB_ORBIT_EPTS(CT, DT, RC_INTERP, 2), SB_ORBIT_EPTS(CT, DT, RC_INTERP, 3),          \
+        SB_ORBIT_EPTS(CT, DT, RC_INTERP, 4)
 const OrbitEntry *orbit_table(int *n)
 {
     static const OrbitEntry tab[] = {SB_ORBIT_TYPE(float, F32), SB_ORBIT_TYPE(double, F64)};

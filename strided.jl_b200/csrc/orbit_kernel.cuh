@@ -78,6 +78,7 @@ map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ 
     constexpr int NT = 1 << LOGT; // consumer threads
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = O.nstage;
+    pdl_launch_dependents();
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 32); // every producer lane arrives: each releases its own item words
@@ -106,8 +107,9 @@ map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ 
                 if (lane + 32 < IW) x1 = src[lane + 32];
             }
         };
-        fetch(blockIdx.x, a0, a1);
+        fetch(blockIdx.x, a0, a1); // (the item table is written once, at plan creation: safe to read before pdl_wait)
         fetch(blockIdx.x + grid, b0, b1);
+        pdl_wait(); // the parent may be the previous kernel's output
         for (uint32_t pos = blockIdx.x; pos < nitems; pos += grid) {
             mbar_wait(smem_u32(&empty_bar[stage]), parity);
             uint32_t *d = item_smem[stage];
@@ -142,6 +144,7 @@ map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ 
         uint32_t parity = 0, sbuf = 0;
         const int K = O.nstaging;
         const int64_t st_t = orbit_store_toff(O, tid);
+        pdl_wait(); // the output may still be read or written by the previous kernel
         for (uint32_t pos = blockIdx.x; pos < nitems; pos += grid) {
             mbar_wait(smem_u32(&full_bar[stage]), parity);
             const OrbitItem *it = reinterpret_cast<const OrbitItem *>(item_smem[stage]);
@@ -198,8 +201,7 @@ template <class CT, int RC, int NIN, int EPT, int LOGT> struct OrbitLaunch {
         auto k = map_orbit_kernel<CT, RC, NIN, EPT, LOGT>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        k<<<grid, (1 << LOGT) + 32, smem, s>>>(O, maps[0], maps[1]);
-        return cudaGetLastError();
+        return launch_pdl(k, grid, (1 << LOGT) + 32, smem, s, O, maps[0], maps[1]);
     }
     static cudaError_t occupancy(int *nb, size_t smem)
     {

@@ -766,6 +766,7 @@ bool orbit_instantiated(int ct, int recipe, int nin, int ept, int logt)
     case RC_ADD2: case RC_ADD2_MUL: case RC_ADD2_DIV: case RC_AXPY: case RC_AXPBY: return nin == 2;
     case RC_SUM3: return nin == 3;
     case RC_SUM4: return nin == 4;
+    case RC_INTERP: return nin >= 2 && nin <= 4; // any other element function over aliased views: in-kernel interpreter
     default: return false;
     }
 }

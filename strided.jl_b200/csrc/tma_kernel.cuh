@@ -131,6 +131,7 @@ map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaP
     const uint32_t ring_u32 = smem_u32(ring);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = T.nstage;
+    pdl_launch_dependents();
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
@@ -165,6 +166,7 @@ map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaP
         }
         int stage = 0;
         uint32_t parity = 1; // a fresh barrier passes a wait on parity 1: every stage starts out empty
+        pdl_wait(); // the operands may be the previous kernel's output
         for (uint32_t pos = blockIdx.x; pos < ntiles; pos += grid) {
             mbar_wait(smem_u32(&empty_bar[stage]), parity);
             const uint32_t fb = smem_u32(&full_bar[stage]);
@@ -209,6 +211,7 @@ map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaP
         tma_thread_init<NIN>(P, T, t, th);
         int stage = 0;
         uint32_t parity = 0;
+        pdl_wait(); // the output may still be read or written by the previous kernel
         for (uint32_t pos = blockIdx.x; pos < ntiles; pos += grid) {
             MapTile<1> tl;
             if (P.tile_desc) {
@@ -244,8 +247,7 @@ template <class CT, int RC, int NIN, int EPT> struct TmaLaunch {
         auto k = map_tma_kernel<CT, RC, NIN, EPT>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        k<<<grid, TMA_THREADS, smem, s>>>(P, T, maps[0], maps[1], maps[2], maps[3]);
-        return cudaGetLastError();
+        return launch_pdl(k, grid, TMA_THREADS, smem, s, P, T, maps[0], maps[1], maps[2], maps[3]);
     }
     static cudaError_t occupancy(int *nb, size_t smem)
     {

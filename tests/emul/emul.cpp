@@ -165,7 +165,7 @@ template <class CT> static bool orbit_dispatch(const Plan &plan, int grid)
         if (ept == 8) { run_orbit<CT, R, N, 8>(plan, grid); return true; }                                           \
         if (ept == 16) { run_orbit<CT, R, N, 16>(plan, grid); return true; }                                         \
     }
-    TRYO(RC_ADD2, 2) TRYO(RC_ADD2_MUL, 2) TRYO(RC_ADD2_DIV, 2) TRYO(RC_AXPY, 2) TRYO(RC_AXPBY, 2) TRYO(RC_SUM3, 3) TRYO(RC_SUM4, 4)
+    TRYO(RC_ADD2, 2) TRYO(RC_ADD2_MUL, 2) TRYO(RC_ADD2_DIV, 2) TRYO(RC_AXPY, 2) TRYO(RC_AXPBY, 2) TRYO(RC_SUM3, 3) TRYO(RC_SUM4, 4) TRYO(RC_INTERP, 2) TRYO(RC_INTERP, 3) TRYO(RC_INTERP, 4)
 #undef TRYO
     return false;
 }

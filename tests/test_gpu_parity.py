@@ -117,3 +117,41 @@ def test_engine_counts_launches_and_caches_plans():
     c.run_gpu("device")
     st = eng.stats()
     assert st["launches"] == 1 and st["plans_cached"] == 1 and st["plans_built"] == 0
+
+
+def test_back_to_back_dependent_launches_are_ordered():
+    """Every kernel is launched with programmatic stream serialisation (PDL): the next kernel's prologue overlaps the
+    previous kernel's tail, and griddepcontrol.wait orders the data accesses.  A chain of DEPENDENT calls without any
+    host synchronisation (each reads what the previous one wrote; the kernel families alternate) must equal NumPy."""
+    import torch
+    rng = np.random.default_rng(7)
+    n = 1024
+    a0 = rng.standard_normal(n * n)
+    bufs = [torch.from_numpy(a0.copy()).cuda(), torch.zeros(n * n, dtype=torch.float64, device="cuda")]
+    acc = torch.zeros(1, dtype=torch.float64, device="cuda")
+    ref = a0.reshape(n, n, order="F").copy()
+    ref_acc = 0.0
+    eng = sb.get_engine(0)
+    eng.set_sync(False)
+    try:
+        for it in range(24):
+            src, dst = bufs[it % 2], bufs[(it + 1) % 2]
+            S, D = sb.StridedView(src, (n, n), (1, n)), sb.StridedView(dst, (n, n), (1, n))
+            if it % 3 == 0:      # TMA ring kernel: D = (S + S') / 2
+                D.assign((S + S.T) / 2)
+                ref = (ref + ref.T) / 2
+            elif it % 3 == 1:    # generic / TMA transpose-scale: D = 3 * S'
+                D.assign(3 * S.T)
+                ref = 3 * ref.T
+            else:                # dense map + a full reduction of the fresh output into a running scalar
+                D.assign(S * 0.25)
+                ref = ref * 0.25
+                sb.run_mapreduce([(0, 0, 0.0, 0.0), (2, sb.abi.FN["abs2"], 0.0, 0.0)], 1, 0, 0.0, (n, n),
+                                 [sb.StridedView(acc, (n, n), (0, 0)), D])
+                ref_acc += float(np.sum(ref * ref))
+        torch.cuda.synchronize()
+    finally:
+        eng.set_sync(True)
+    got = bufs[24 % 2].cpu().numpy().reshape(n, n, order="F")
+    np.testing.assert_allclose(got, ref, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(acc.item(), ref_acc, rtol=1e-10)

@@ -54,6 +54,9 @@ def orbit_cases(big=False):
         Av = ViewSpec.dense(1, (n,) * 3)
         out.append((Case(f"orbit_sum3_{nm}", [b, a], [ViewSpec.dense(0, (n,) * 3), Av, Av.permutedims((1, 2, 0)), Av.permutedims((2, 0, 1))],
                          [A(0), A(1), F("add"), A(2), F("add")]), True))
+        # a non-recipe element function over three aliased views: x * y' - z''  (in-kernel interpreter inside the fused kernel)
+        out.append((Case(f"orbit_interp3_{nm}", [b.copy(), a], [ViewSpec.dense(0, (n,) * 3), Av, Av.permutedims((1, 2, 0)), Av.permutedims((2, 0, 1))],
+                         [A(0), A(1), F("mul"), A(2), F("sub")]), True))
         # C4 family (edge tiles for 20)
         for n in (16, 20):
             c = case_c4(n, dt)

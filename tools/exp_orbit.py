@@ -17,14 +17,13 @@ from tools.profile_case import MAKE  # noqa: E402
 
 N2 = {"SB_ORBIT_NIN2": "1"}
 VARIANTS = {
-    "c2": [{}, dict(N2), dict(N2, SB_ORBIT_STAGES="3")],
-    "c4": [{}, {"SB_ORBIT_LOGT": "8"}, {"SB_ORBIT_STAGING": "3"}, {"SB_ORBIT_SUPER": "0"}, {"SB_ORBIT_SUPER": "1"}, {"SB_ORBIT_SUPER": "3"},
-           {"SB_ORBIT_LOGT": "8", "SB_ORBIT_STAGES": "1", "SB_ORBIT_STAGING": "2"},
-           {"SB_DEBUG": "noload,nostore"}, {"SB_ORBIT_LOGT": "8", "SB_DEBUG": "noload,nostore"}, {"SB_DEBUG": "nocompute"},
-           {"SB_DEBUG": "noload,nostore,nocompute"}],
-    "c4p": [{}, {"SB_ORBIT_LOGT": "8"}],
-    "c1": [{}],
-    "c3": [{}],
+    "c2": [{}, {"SB_NO_PDL": "1"}, dict(N2)],
+    "c4": [{}, {"SB_NO_PDL": "1"}],
+    "c4p": [{}, {"SB_NO_PDL": "1"}],
+    "c1": [{}, {"SB_NO_PDL": "1"}],
+    "c3": [{}, {"SB_NO_PDL": "1"}],
+    "c5": [{}, {"SB_NO_PDL": "1"}],
+    "c5shard": [{}, {"SB_NO_PDL": "1"}],
 }
 
 
