@@ -61,7 +61,22 @@ template <class AT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forcein
     pdl_wait(); // (the previous launch may be a reduction re-arming the same arrival counters)
     red_accumulate<AT, RC, NIN, EPT, UNIFORM>(P, bid, t, smem);
     __syncthreads();
-    if (P.warp_per_output) {
+    if (P.warp_per_output && P.nout_tile == 1) {
+        // a single output per CTA: all eight warps fold the THREADS*EPT accumulators (layout [0][r]), fixed order
+        const int warp = t >> 5, lane = t & 31;
+        AT p = red_neutral<AT>(P.op);
+        for (int r = t; r < P.nred_tile; r += THREADS) p = red_apply<AT>(P.op, p, smem[r]);
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) p = red_apply<AT>(P.op, p, shfl_xor_any(p, m));
+        __syncthreads();
+        if (lane == 0) smem[warp] = p;
+        __syncthreads();
+        if (t == 0) {
+            AT q = smem[0];
+            for (int w = 1; w < THREADS / 32; ++w) q = red_apply<AT>(P.op, q, smem[w]);
+            red_finish<AT, UNIFORM>(P, bid, 0, q);
+        }
+    } else if (P.warp_per_output) {
         const int warp = t >> 5, lane = t & 31;
         for (int o = warp; o < P.nout_tile; o += THREADS / 32) {
             AT p = red_lane_partial<AT>(P, smem, o, lane);
@@ -85,12 +100,40 @@ template <class AT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forcein
         if (sb_is_last) {
             __threadfence();
             const int warp = t >> 5, lane = t & 31;
-            for (int o = warp; o < P.nout_tile; o += THREADS / 32) {
-                const int64_t out_idx = (int64_t)out_tile * P.nout_tile + o;
-                AT p = red_finalize_lane<AT>(P, out_idx, lane);
+            if (P.nout_tile == 1) {
+                // one output (complete reductions; config 5 per GPU): ALL eight warps fold -- thread t takes the splits
+                // t, t+256, ... (eight L2 loads in flight), warp butterfly, then the eight warp results in warp order.
+                // Same fixed order on every run; with one warp the 586 partials of a 128 MiB shard took three dependent
+                // L2 round trips.
+                const AT *sc = reinterpret_cast<const AT *>(P.scratch);
+                const int64_t stride = P.nouttiles;
+                AT p = red_neutral<AT>(P.op);
+                for (int s0 = t; s0 < P.nsplit; s0 += 8 * THREADS) {
+                    AT v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        v[u] = (s0 + THREADS * u < P.nsplit) ? load_partial(sc + (int64_t)(s0 + THREADS * u) * stride + out_tile) : red_neutral<AT>(P.op);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) p = red_apply<AT>(P.op, p, v[u]);
+                }
 #pragma unroll
                 for (int m = 16; m >= 1; m >>= 1) p = red_apply<AT>(P.op, p, shfl_xor_any(p, m));
-                if (lane == 0) red_finalize_store<AT, UNIFORM>(P, out_idx, p);
+                __syncthreads(); // the accumulators in `smem` have been consumed by red_finish above
+                if (lane == 0) smem[warp] = p;
+                __syncthreads();
+                if (t == 0) {
+                    AT q = smem[0];
+                    for (int w = 1; w < THREADS / 32; ++w) q = red_apply<AT>(P.op, q, smem[w]);
+                    red_finalize_store<AT, UNIFORM>(P, (int64_t)out_tile, q);
+                }
+            } else {
+                for (int o = warp; o < P.nout_tile; o += THREADS / 32) {
+                    const int64_t out_idx = (int64_t)out_tile * P.nout_tile + o;
+                    AT p = red_finalize_lane<AT>(P, out_idx, lane);
+#pragma unroll
+                    for (int m = 16; m >= 1; m >>= 1) p = red_apply<AT>(P.op, p, shfl_xor_any(p, m));
+                    if (lane == 0) red_finalize_store<AT, UNIFORM>(P, out_idx, p);
+                }
             }
             if (t == 0) P.counters[out_tile] = 0u; // re-arm for the next launch
         }
