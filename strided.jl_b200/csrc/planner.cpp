@@ -907,7 +907,7 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
         ntile[d] = (c.dims[d] + ((int64_t)1 << tb[d]) - 1) >> tb[d];
         ntiles *= ntile[d];
     }
-    if (ntiles < 2 || ntiles > (1 << 22)) return false;
+    if (ntiles < 2 || ntiles > (1 << 18)) return false; // (one 216-byte record per orbit lives on the device with the plan)
     auto decode = [&](int64_t id, int64_t *cc) {
         for (int d = 0; d < n; ++d) {
             cc[d] = id % ntile[d];
@@ -1234,10 +1234,12 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
         return (double)(((c.dims[i] + t - 1) / t) * t) / (double)c.dims[i];
     };
     int lim[MAXD];
+    double max_waste = 1.2;
+    if (const char *e = std::getenv("SB_WASTE")) max_waste = std::max(1.0, std::atof(e)); // tuning knob
     for (int i = 0; i < n; ++i) {
         const int lo = hot[i] ? std::min(cap[i], minrun_bits) : 0;
         int bbits = cap[i];
-        while (bbits > lo && waste_of(i, bbits) > 1.2) --bbits;
+        while (bbits > lo && waste_of(i, bbits) > max_waste) --bbits;
         lim[i] = bbits;
     }
     auto ntile_dims = [&]() {
