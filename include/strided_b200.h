@@ -155,6 +155,30 @@ int sb_mapreduce(sb_ctx *ctx, const sb_desc *desc);
  * range back.  This is the end-to-end entry `bench.py` times as "e2e". */
 int sb_mapreduce_host(sb_ctx *ctx, const sb_desc *desc);
 
+/* ---- reductions across GPUs (one process per GPU) --------------------------------------------------
+ * GPU analog of the per-task partial slots + serial fold of a threaded complete reduction
+ * (`threadedout`, src/mapreduce.jl:153-170): every rank reduces ITS slab, the partials of all ranks are exchanged
+ * through peer memory over NVLink by a kernel of this library (no NCCL call on the path) and folded in RANK ORDER on
+ * every rank, so all ranks obtain bit-identical results:
+ *
+ *     out_r = op(initop(out_r), partial_0 (op) partial_1 (op) ... (op) partial_{world-1})
+ *
+ *   sb_peer_export  allocates this rank's exchange buffer and returns its 64-byte CUDA IPC handle;
+ *   sb_peer_attach  takes the handles of ALL ranks (world * 64 bytes, rank order; exchanged by the host program,
+ *                   e.g. torch.distributed.all_gather_object / MPI) and maps the peers' buffers;
+ *   sb_mapreduce_allreduce  is COLLECTIVE: every attached rank must call it, in the same order, with descriptors whose
+ *                   OUTPUT has the same number of elements (<= SB_PEER_MAX_OUT) and dtype.  `desc` describes the local
+ *                   reduction exactly as for sb_mapreduce (device pointers; a zero-size local slab contributes the
+ *                   neutral element).  world == 1 (or not attached): identical to sb_mapreduce.
+ * A rank that waits longer than ~2 s for a peer traps (SB_E_CUDA) instead of hanging the GPU. */
+#define SB_PEER_MAX_OUT 1024
+#define SB_PEER_MAX_WORLD 8
+#define SB_IPC_HANDLE_BYTES 64
+int sb_peer_export(sb_ctx *ctx, unsigned char handle_out[SB_IPC_HANDLE_BYTES]);
+int sb_peer_attach(sb_ctx *ctx, int rank, int world, const unsigned char *handles /* world * 64 bytes */);
+int sb_peer_detach(sb_ctx *ctx);
+int sb_mapreduce_allreduce(sb_ctx *ctx, const sb_desc *desc);
+
 /* ---- introspection (no GPU needed) --------------------------------------------------------------
  * Writes a one-line JSON description of the plan the host planner picks for `desc` (kernel family,
  * canonical dims, tile extents, staged operands, grid) into buf.  ctx may be NULL. */

@@ -78,7 +78,9 @@ EXPORTS = [
     "sb_abi_version", "sb_ctx_create", "sb_ctx_destroy", "sb_ctx_set_stream", "sb_ctx_set_sync", "sb_sync",
     "sb_last_error", "sb_malloc", "sb_free", "sb_memcpy_h2d", "sb_memcpy_d2h", "sb_mapreduce",
     "sb_mapreduce_host", "sb_plan_describe", "sb_get_stats", "sb_reset_stats",
+    "sb_peer_export", "sb_peer_attach", "sb_peer_detach", "sb_mapreduce_allreduce",
 ]
+SB_PEER_MAX_OUT, SB_PEER_MAX_WORLD, SB_IPC_HANDLE_BYTES = 1024, 8, 64
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libstrided_b200.so")
@@ -113,6 +115,10 @@ def load_library():
     lib.sb_plan_describe.argtypes = [vp, C.POINTER(sb_desc), C.c_char_p, C.c_size_t]
     lib.sb_get_stats.argtypes = [vp, C.POINTER(sb_stats)]
     lib.sb_reset_stats.argtypes = [vp]
+    lib.sb_peer_export.argtypes = [vp, C.c_char_p]
+    lib.sb_peer_attach.argtypes = [vp, i32, i32, C.c_char_p]
+    lib.sb_peer_detach.argtypes = [vp]
+    lib.sb_mapreduce_allreduce.argtypes = [vp, C.POINTER(sb_desc)]
     for n in EXPORTS:
         if n != "sb_last_error":
             getattr(lib, n).restype = i32

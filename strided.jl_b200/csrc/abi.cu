@@ -5,6 +5,7 @@
 #include "orbit_kernel.cuh"
 #include "jit.hpp"
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -154,6 +155,12 @@ struct sb_ctx {
     void *stage = nullptr;
     size_t stage_bytes = 0;
     std::unordered_map<std::string, CachedPlan> plans;
+    // peer group for reductions across GPUs (sb_peer_*): exchange buffers of all ranks, mapped through CUDA IPC
+    int peer_rank = 0, peer_world = 1;
+    uint32_t peer_epoch = 0;
+    void *peer_local = nullptr;                  // this rank's buffer (cudaMalloc)
+    void *peer_buf[SB_PEER_MAX_WORLD] = {nullptr}; // [g] = rank g's buffer as seen from this process
+    void *peer_tmp = nullptr;                    // local partial (SB_PEER_MAX_OUT elements of up to 16 bytes)
 };
 
 static void clear_plans(sb_ctx *ctx)
@@ -235,6 +242,9 @@ int sb_ctx_destroy(sb_ctx *ctx)
     clear_plans(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->stage) cudaFree(ctx->stage);
+    sb_peer_detach(ctx);
+    if (ctx->peer_local) cudaFree(ctx->peer_local);
+    if (ctx->peer_tmp) cudaFree(ctx->peer_tmp);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SB_OK;
@@ -601,6 +611,265 @@ extern "C" int sb_mapreduce(sb_ctx *ctx, const sb_desc *desc)
     if (ctx->sync) {
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) return cuda_fail(ctx, e, "kernel execution");
+    }
+    return SB_OK;
+}
+
+// ---- reductions across GPUs through peer memory (no NCCL on the path) -------------------------------------------
+// Exchange buffer of a rank:  [flag of rank 0 | ... | flag of rank 7]  (128 bytes apart)  then
+// data[parity][rank][SB_PEER_MAX_OUT] in 16-byte slots.  Rank r pushes its partial into slot [epoch & 1][r] of EVERY
+// rank's buffer (plain stores to mapped peer memory: NVLink), fences, raises flag r in every buffer to `epoch`, waits
+// until its own buffer shows all flags >= epoch, then folds the world partials in rank order.  Two parities because a
+// fast rank may already push call n+1 while a slow one still folds call n (it cannot be two calls ahead: it needs the
+// slow rank's flag of call n+1 first).
+namespace {
+constexpr size_t PEER_FLAG_STRIDE = 128;
+constexpr size_t PEER_DATA_OFF = SB_PEER_MAX_WORLD * PEER_FLAG_STRIDE;
+constexpr size_t PEER_SLOT = 16;
+constexpr size_t PEER_BUF_BYTES = PEER_DATA_OFF + 2 * (size_t)SB_PEER_MAX_WORLD * SB_PEER_MAX_OUT * PEER_SLOT;
+
+struct PeerKernelParams {
+    int32_t world, rank, nout, op, initop, local_empty, nkept, out_dtype, out_conj;
+    uint32_t epoch;
+    double init_re, init_im;
+    int64_t kdims[MAXD], kstr_bytes[MAXD]; // kept dims of the output view and their byte strides
+    unsigned char *buf[SB_PEER_MAX_WORLD];
+    const unsigned char *tmp; // this rank's partial: dense, element type = output dtype
+    unsigned char *out;
+};
+
+template <class AT> __global__ void __launch_bounds__(256) peer_allreduce_kernel(const __grid_constant__ PeerKernelParams K)
+{
+    constexpr int W = sizeof(AT) / 4;
+    const int t = threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait(); // the local reduction wrote K.tmp
+    const size_t par = (size_t)(K.epoch & 1u) * SB_PEER_MAX_WORLD;
+    if (W <= 2) {
+        // Low-latency path for 4- and 8-byte elements: every 32-bit half travels in ONE 8-byte store together with the
+        // epoch ({word, epoch}; 8-byte stores to peer memory are delivered atomically), so the receiver needs no flag,
+        // no fence and no barrier: each thread pushes its element to all ranks and then polls its own copies.
+        for (int o = t; o < K.nout; o += 256) {
+            union {
+                AT v;
+                uint32_t w[2];
+            } u;
+            u.w[1] = 0u;
+            u.v = K.local_empty ? red_neutral<AT>(K.op) : reinterpret_cast<const AT *>(K.tmp)[o];
+            const size_t off = PEER_DATA_OFF + ((par + (size_t)K.rank) * SB_PEER_MAX_OUT + (size_t)o) * PEER_SLOT;
+            for (int g = 0; g < K.world; ++g) {
+                unsigned char *dst = K.buf[g] + off;
+                asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(u.w[0]), "r"(K.epoch) : "memory");
+                asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst + 8), "r"(u.w[1]), "r"(K.epoch) : "memory");
+            }
+            AT tot = red_neutral<AT>(K.op);
+            const long long t0 = clock64();
+            for (int g = 0; g < K.world; ++g) {
+                const unsigned char *src = K.buf[K.rank] + PEER_DATA_OFF + ((par + (size_t)g) * SB_PEER_MAX_OUT + (size_t)o) * PEER_SLOT;
+                uint32_t a0, e0, a1, e1;
+                for (;;) {
+                    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(a0), "=r"(e0) : "l"(src) : "memory");
+                    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(a1), "=r"(e1) : "l"(src + 8) : "memory");
+                    if (e0 == K.epoch && e1 == K.epoch) break;
+                    if (clock64() - t0 > 4000000000LL) __trap(); // a missing peer must not hang the GPU
+                }
+                u.w[0] = a0;
+                u.w[1] = a1;
+                tot = g == 0 ? u.v : red_apply<AT>(K.op, tot, u.v);
+            }
+            int64_t ooff = 0;
+            int rem = o;
+            for (int d = 0; d < K.nkept; ++d) {
+                const int c = rem % (int)K.kdims[d];
+                rem /= (int)K.kdims[d];
+                ooff += (int64_t)c * K.kstr_bytes[d];
+            }
+            AT x = load_elem<AT, false>(K.out + ooff, K.out_dtype, K.out_conj);
+            x = init_apply<AT>(K.initop, K.init_re, K.init_im, x);
+            store_elem<AT, false>(K.out + ooff, K.out_dtype, K.out_conj, red_apply<AT>(K.op, x, tot));
+        }
+        return;
+    }
+    for (int o = t; o < K.nout; o += 256) {
+        union {
+            AT v;
+            uint32_t w[W];
+        } u;
+        u.v = K.local_empty ? red_neutral<AT>(K.op) : reinterpret_cast<const AT *>(K.tmp)[o];
+        const size_t off = PEER_DATA_OFF + ((par + (size_t)K.rank) * SB_PEER_MAX_OUT + (size_t)o) * PEER_SLOT;
+        for (int g = 0; g < K.world; ++g) {
+            volatile uint32_t *dst = reinterpret_cast<volatile uint32_t *>(K.buf[g] + off);
+#pragma unroll
+            for (int i = 0; i < W; ++i) dst[i] = u.w[i];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < K.world) { // thread g: tell rank g that this rank's partial has landed, then wait for rank g's
+        *reinterpret_cast<volatile uint32_t *>(K.buf[t] + PEER_FLAG_STRIDE * (size_t)K.rank) = K.epoch;
+        volatile uint32_t *f = reinterpret_cast<volatile uint32_t *>(K.buf[K.rank] + PEER_FLAG_STRIDE * (size_t)t);
+        const long long t0 = clock64();
+        while ((int32_t)(*f - K.epoch) < 0)
+            if (clock64() - t0 > 4000000000LL) __trap(); // a missing peer must not hang the GPU
+    }
+    __threadfence_system();
+    __syncthreads();
+    for (int o = t; o < K.nout; o += 256) {
+        AT tot = red_neutral<AT>(K.op);
+        for (int g = 0; g < K.world; ++g) {
+            union {
+                AT v;
+                uint32_t w[W];
+            } u;
+            const volatile uint32_t *src = reinterpret_cast<const volatile uint32_t *>(
+                K.buf[K.rank] + PEER_DATA_OFF + ((par + (size_t)g) * SB_PEER_MAX_OUT + (size_t)o) * PEER_SLOT);
+#pragma unroll
+            for (int i = 0; i < W; ++i) u.w[i] = src[i];
+            tot = g == 0 ? u.v : red_apply<AT>(K.op, tot, u.v);
+        }
+        int64_t off = 0;
+        int rem = o;
+        for (int d = 0; d < K.nkept; ++d) {
+            const int c = rem % (int)K.kdims[d];
+            rem /= (int)K.kdims[d];
+            off += (int64_t)c * K.kstr_bytes[d];
+        }
+        AT x = load_elem<AT, false>(K.out + off, K.out_dtype, K.out_conj);
+        x = init_apply<AT>(K.initop, K.init_re, K.init_im, x);
+        store_elem<AT, false>(K.out + off, K.out_dtype, K.out_conj, red_apply<AT>(K.op, x, tot));
+    }
+}
+} // namespace
+
+extern "C" int sb_peer_export(sb_ctx *ctx, unsigned char handle_out[SB_IPC_HANDLE_BYTES])
+{
+    if (!ctx || !handle_out) return set_err(ctx, SB_E_INVALID, "sb_peer_export: null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaSetDevice(ctx->device);
+    if (!ctx->peer_local) {
+        cudaError_t e = cudaMalloc(&ctx->peer_local, PEER_BUF_BYTES);
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->peer_tmp, (size_t)SB_PEER_MAX_OUT * PEER_SLOT);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(peer buffer)");
+    }
+    cudaError_t e = cudaMemset(ctx->peer_local, 0, PEER_BUF_BYTES);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMemset(peer buffer)");
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(cudaIpcMemHandle_t) == SB_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+    e = cudaIpcGetMemHandle(&h, ctx->peer_local);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaIpcGetMemHandle");
+    std::memcpy(handle_out, &h, sizeof h);
+    ctx->peer_epoch = 0;
+    return SB_OK;
+}
+
+extern "C" int sb_peer_detach(sb_ctx *ctx)
+{
+    if (!ctx) return SB_OK;
+    for (int g = 0; g < SB_PEER_MAX_WORLD; ++g) {
+        if (ctx->peer_buf[g] && ctx->peer_buf[g] != ctx->peer_local) cudaIpcCloseMemHandle(ctx->peer_buf[g]);
+        ctx->peer_buf[g] = nullptr;
+    }
+    ctx->peer_world = 1;
+    ctx->peer_rank = 0;
+    return SB_OK;
+}
+
+extern "C" int sb_peer_attach(sb_ctx *ctx, int rank, int world, const unsigned char *handles)
+{
+    if (!ctx || !handles) return set_err(ctx, SB_E_INVALID, "sb_peer_attach: null argument");
+    if (world < 1 || world > SB_PEER_MAX_WORLD || rank < 0 || rank >= world) return set_err(ctx, SB_E_INVALID, "sb_peer_attach: bad rank/world");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->peer_local) return set_err(ctx, SB_E_INVALID, "sb_peer_attach: call sb_peer_export first");
+    cudaSetDevice(ctx->device);
+    sb_peer_detach(ctx);
+    for (int g = 0; g < world; ++g) {
+        if (g == rank) {
+            ctx->peer_buf[g] = ctx->peer_local;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + (size_t)g * SB_IPC_HANDLE_BYTES, sizeof h);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            sb_peer_detach(ctx);
+            return cuda_fail(ctx, e, "cudaIpcOpenMemHandle (peer exchange buffer)");
+        }
+        ctx->peer_buf[g] = p;
+    }
+    ctx->peer_rank = rank;
+    ctx->peer_world = world;
+    ctx->peer_epoch = 0;
+    return SB_OK;
+}
+
+extern "C" int sb_mapreduce_allreduce(sb_ctx *ctx, const sb_desc *desc)
+{
+    if (!ctx) return set_err(nullptr, SB_E_INVALID, "sb_mapreduce_allreduce: null ctx");
+    if (!desc) return set_err(ctx, SB_E_INVALID, "sb_mapreduce_allreduce: null desc");
+    if (ctx->peer_world <= 1) return sb_mapreduce(ctx, desc);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const sb_desc &d = *desc;
+    if (d.ndim < 0 || d.ndim > SB_MAX_DIMS || d.nops < 2 || d.nops > SB_MAX_OPS) return set_err(ctx, SB_E_INVALID, "bad ndim/nops");
+    if (d.op < SB_OP_ADD || d.op > SB_OP_MAX) return set_err(ctx, SB_E_INVALID, "sb_mapreduce_allreduce needs a reduction operator");
+    if (d.dtype[0] < SB_F32 || d.dtype[0] > SB_C64) return set_err(ctx, SB_E_INVALID, "bad dtype");
+    PeerKernelParams K;
+    std::memset(&K, 0, sizeof K);
+    int64_t nout = 1, dense = 1;
+    bool empty = false;
+    sb_desc loc = d; // the local reduction into the dense temporary, started from the neutral element
+    for (int i = 0; i < d.ndim; ++i) {
+        if (d.dims[i] < 0) return set_err(ctx, SB_E_SHAPE, "negative dim");
+        if (d.dims[i] == 0) empty = true;
+        const bool kept = d.strides[0][i] != 0 && d.dims[i] != 1;
+        loc.strides[0][i] = kept ? dense : 0;
+        if (kept) {
+            K.kdims[K.nkept] = d.dims[i];
+            K.kstr_bytes[K.nkept] = d.strides[0][i] * (int64_t)dtype_size(d.dtype[0]);
+            K.nkept++;
+            dense *= d.dims[i];
+            nout *= d.dims[i];
+        }
+    }
+    if (nout > SB_PEER_MAX_OUT) return set_err(ctx, SB_E_UNSUPPORTED, "sb_mapreduce_allreduce: more than SB_PEER_MAX_OUT outputs");
+    cudaSetDevice(ctx->device);
+    const double neutral = d.op == SB_OP_ADD ? 0.0 : d.op == SB_OP_MUL ? 1.0 : d.op == SB_OP_MIN ? (double)INFINITY : -(double)INFINITY;
+    if (!empty) {
+        loc.base[0] = ctx->peer_tmp;
+        loc.conj[0] = 0;
+        loc.initop = SB_INIT_CONST;
+        loc.init_re = neutral;
+        loc.init_im = 0.0;
+        const int rc = run_desc(ctx, loc);
+        if (rc != SB_OK) return rc; // (every rank sees the same program and dtypes: a planning error is collective)
+    }
+    K.world = ctx->peer_world;
+    K.rank = ctx->peer_rank;
+    K.nout = (int32_t)nout;
+    K.op = d.op;
+    K.initop = d.initop;
+    K.init_re = d.init_re;
+    K.init_im = d.init_im;
+    K.local_empty = empty ? 1 : 0;
+    K.out_dtype = d.dtype[0];
+    K.out_conj = d.conj[0] && (d.dtype[0] == SB_C32 || d.dtype[0] == SB_C64);
+    K.epoch = ++ctx->peer_epoch;
+    for (int g = 0; g < ctx->peer_world; ++g) K.buf[g] = (unsigned char *)ctx->peer_buf[g];
+    K.tmp = (const unsigned char *)ctx->peer_tmp;
+    K.out = (unsigned char *)d.base[0];
+    cudaError_t e;
+    switch (d.dtype[0]) {
+    case SB_F32: e = launch_pdl(peer_allreduce_kernel<float>, 1, 256, 0, ctx->stream, K); break;
+    case SB_F64: e = launch_pdl(peer_allreduce_kernel<double>, 1, 256, 0, ctx->stream, K); break;
+    case SB_C32: e = launch_pdl(peer_allreduce_kernel<cx<float>>, 1, 256, 0, ctx->stream, K); break;
+    default: e = launch_pdl(peer_allreduce_kernel<cx<double>>, 1, 256, 0, ctx->stream, K); break;
+    }
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "peer_allreduce launch");
+    ctx->stats.launches++;
+    if (ctx->sync) {
+        e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "sb_mapreduce_allreduce");
     }
     return SB_OK;
 }

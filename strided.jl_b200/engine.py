@@ -36,6 +36,7 @@ class Engine:
         self.ctx = ctx
         self._stream = None
         self.sync = True
+        self.peer_world = 1
 
     def close(self):
         if self.ctx:
@@ -61,6 +62,25 @@ class Engine:
 
     def reset_stats(self):
         abi.check(self.lib, self.ctx, self.lib.sb_reset_stats(self.ctx))
+
+    # ---- peer group (reductions across GPUs through peer memory, include/strided_b200.h "sb_peer_*") ----
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(abi.SB_IPC_HANDLE_BYTES)
+        abi.check(self.lib, self.ctx, self.lib.sb_peer_export(self.ctx, buf))
+        return buf.raw
+
+    def peer_attach(self, rank: int, world: int, handles):
+        blob = b"".join(handles)
+        assert len(blob) == world * abi.SB_IPC_HANDLE_BYTES
+        abi.check(self.lib, self.ctx, self.lib.sb_peer_attach(self.ctx, int(rank), int(world), blob))
+        self.peer_world = int(world)
+
+    def peer_detach(self):
+        abi.check(self.lib, self.ctx, self.lib.sb_peer_detach(self.ctx))
+        self.peer_world = 1
+
+    def mapreduce_allreduce(self, desc: abi.sb_desc):
+        abi.check(self.lib, self.ctx, self.lib.sb_mapreduce_allreduce(self.ctx, C.byref(desc)))
 
     def mapreduce(self, desc: abi.sb_desc, host: bool):
         fn = self.lib.sb_mapreduce_host if host else self.lib.sb_mapreduce
@@ -101,7 +121,7 @@ def make_desc(tokens, op, initop, init, dims, views) -> abi.sb_desc:
     return d
 
 
-def run_mapreduce(tokens, op, initop, init, dims, views, engine=None):
+def run_mapreduce(tokens, op, initop, init, dims, views, engine=None, allreduce=False):
     """_mapreduce_fuse!(f, op, initop, dims, arrays) on the device (reference src/mapreduce.jl:98-99).
 
     `engine`: an explicit :class:`Engine` (its own ctx + stream), e.g. two of them to overlap the H2D of one call
@@ -116,8 +136,13 @@ def run_mapreduce(tokens, op, initop, init, dims, views, engine=None):
         eng = engine or get_engine(idx)
         if engine is None:
             eng.set_stream(torch.cuda.current_stream(idx).cuda_stream)
-        eng.mapreduce(desc, host=False)
+        if allreduce:  # collective over the engine's peer group (sb_mapreduce_allreduce)
+            eng.mapreduce_allreduce(desc)
+        else:
+            eng.mapreduce(desc, host=False)
     else:  # host parents (plain `Array`s): staged through the device by sb_mapreduce_host
+        if allreduce:
+            raise ValueError("allreduce=True needs device-resident operands")
         eng = engine or get_engine(0)
         eng.mapreduce(desc, host=True)
     return views[0]

@@ -43,6 +43,23 @@ def shard_view(A: StridedView, dim: int, rank: int, world: int) -> StridedView:
     return A[idx]
 
 
+def attach_peer_group(group=None, device=None):
+    """Map every rank's exchange buffer into this process (CUDA IPC; handles travel through torch.distributed) so that
+    reductions over the sharded dim are combined by the library's own kernel over NVLink peer memory instead of an
+    NCCL all-reduce (include/strided_b200.h: sb_peer_export / sb_peer_attach / sb_mapreduce_allreduce).  Collective."""
+    from .engine import get_engine
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world > abi.SB_PEER_MAX_WORLD:
+        raise abi.UnsupportedError(abi.SB_E_UNSUPPORTED, f"peer groups span one NVSwitch domain (<= {abi.SB_PEER_MAX_WORLD} GPUs)")
+    eng = get_engine(torch.cuda.current_device() if device is None else device)
+    handles = [None] * world
+    dist.all_gather_object(handles, eng.peer_export(), group=group)
+    eng.peer_attach(rank, world, handles)
+    dist.barrier(group)  # nobody pushes into a buffer that is still being reset
+    return eng
+
+
 _REDOP = {abi.SB_OP_ADD: "SUM", abi.SB_OP_MUL: "PRODUCT", abi.SB_OP_MIN: "MIN", abi.SB_OP_MAX: "MAX"}
 
 
@@ -57,13 +74,15 @@ def _neutral_fill(out, opc):
         _fill_scalar(out, float("-inf"))
 
 
-def sharded_mapreduce(f, op, A_local, dims=None, shard_dim=None, group=None, compute=None, alloc=None, fill=None):
+def sharded_mapreduce(f, op, A_local, dims=None, shard_dim=None, group=None, compute=None, alloc=None, fill=None, fused=None):
     """mapreduce(f, op, A; dims) where `A_local` is this rank's slab of A along `shard_dim`.
 
     dims=None  : complete reduction -> Python scalar on every rank (one all-reduce of ONE element).
     dims given : `shard_dim in dims`  -> partial of the full output per rank + one all-reduce of #outputs elements;
                  otherwise           -> the rank's own slab of the output, no collective.
     `compute`, `alloc`, `fill` are injection points for the CPU (gloo) tests; the product path uses the CUDA engine.
+    `fused`: combine the ranks' partials with the library's peer-memory kernel (needs `attach_peer_group`) instead of
+    an NCCL all-reduce; default: whenever the engine has a peer group and the output is small enough.
     """
     A_local = maybestrided(A_local)
     compute = compute or _mapreducedim_
@@ -75,11 +94,30 @@ def sharded_mapreduce(f, op, A_local, dims=None, shard_dim=None, group=None, com
     red = tuple(range(n)) if dims is None else ((dims,) if isinstance(dims, int) else tuple(int(d) for d in dims))
     outsize = tuple(1 if d in red else s for d, s in enumerate(A_local.size))
     out = alloc(A_local, result_dtype(tokens, [A_local]), outsize)
+    exchange = shard_dim is None or shard_dim in red
+    world = dist.get_world_size(group) if (dist is not None and dist.is_initialized()) else 1
+    nout = 1
+    for s_ in outsize:
+        nout *= s_
+    if fused is None:
+        fused = False
+        if compute is _mapreducedim_ and exchange and world > 1 and A_local.is_device and nout <= abi.SB_PEER_MAX_OUT:
+            from .engine import get_engine
+            fused = get_engine(torch.cuda.current_device()).peer_world == world
+    if fused and exchange and world > 1:
+        # ONE call: local reduction + exchange of the partials through peer memory + fold in rank order, all ranks;
+        # initop = x -> neutral element, so the (uninitialised) output needs no separate fill
+        from .broadcast import promoteshape
+        from .engine import run_mapreduce
+        neutral = {abi.SB_OP_ADD: 0.0, abi.SB_OP_MUL: 1.0, abi.SB_OP_MIN: float("inf"), abi.SB_OP_MAX: float("-inf")}[opc]
+        views = promoteshape(A_local.size, out, A_local)
+        run_mapreduce(tokens, opc, abi.SB_INIT_CONST, neutral, A_local.size, views, allreduce=True)
+        if dims is None:
+            return out.to_numpy().reshape(-1)[0].item()
+        return out
     fill(out, opc)  # neutral element: every rank contributes op-partials only
     if len(A_local) > 0:
         compute(tokens, opc, None, A_local.size, (out, A_local))
-    exchange = shard_dim is None or shard_dim in red
-    world = dist.get_world_size(group) if (dist is not None and dist.is_initialized()) else 1
     if exchange and world > 1:
         t = out.parent if torch is not None and isinstance(out.parent, torch.Tensor) else torch.from_numpy(out.parent)
         dist.all_reduce(t, op=getattr(dist.ReduceOp, _REDOP[opc]), group=group)  # the single collective of the path

@@ -34,6 +34,43 @@ def _check(rank, world, device):
     s = sharded.sharded_mapreduce("identity", "+", loc2, shard_dim=2)
     assert abs(s - full.sum()) < 1e-8
     assert sharded.sharded_mapreduce("abs", "max", loc2, shard_dim=2) == np.abs(full).max()
+    if world > 1:
+        _check_fused(rank, world, device, loc2, A3, full)
+
+
+def _check_fused(rank, world, device, loc2, A3, full):
+    """the same reductions with the partials combined by the library's peer-memory kernel (no NCCL on the path)"""
+    import torch
+    import torch.distributed as dist
+    from strided_jl_b200 import sharded
+    eng = sharded.attach_peer_group()
+    assert eng.peer_world == world
+    launches0 = eng.stats()["launches"]
+    out = sharded.sharded_mapreduce("abs2", "+", loc2, dims=(1, 2), shard_dim=2)           # 8 outputs, fused by default now
+    np.testing.assert_allclose(out.to_numpy().reshape(-1), (A3 ** 2).sum(axis=(1, 2)), rtol=1e-12)
+    assert eng.stats()["launches"] - launches0 == 2, "local reduction + peer exchange kernel"
+    unfused = sharded.sharded_mapreduce("abs2", "+", loc2, dims=(1, 2), shard_dim=2, fused=False)
+    np.testing.assert_allclose(out.to_numpy(), unfused.to_numpy(), rtol=1e-13)
+    s = sharded.sharded_mapreduce("identity", "+", loc2, shard_dim=2)
+    assert abs(s - full.sum()) < 1e-8
+    assert sharded.sharded_mapreduce("abs", "max", loc2, shard_dim=2) == np.abs(full).max()
+    assert sharded.sharded_mapreduce("identity", "min", loc2, shard_dim=2) == full.min()
+    # every rank folds the same partials in the same (rank) order: bit-identical results everywhere
+    mine = torch.tensor([s], dtype=torch.float64, device=device)
+    both = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(both, mine)
+    assert all(torch.equal(b, both[0]) for b in both)
+    # many calls back to back without host synchronisation (epochs, slot parity), accumulating into the same output
+    acc = torch.zeros(1, dtype=torch.float64, device=device)
+    O = sb.StridedView(acc, loc2.size, (0, 0, 0))
+    prog = [(0, 0, 0.0, 0.0), (2, sb.abi.FN["abs2"], 0.0, 0.0)]
+    eng.set_sync(False)
+    for _ in range(25):
+        sb.run_mapreduce(prog, 1, 0, 0.0, loc2.size, [O, loc2], allreduce=True)  # acc = acc + sum over ALL ranks
+    torch.cuda.synchronize()
+    eng.set_sync(True)
+    np.testing.assert_allclose(acc.item(), 25 * (full ** 2).sum(), rtol=1e-12)
+    eng.peer_detach()
 
 
 def _worker(rank, world, port, q):
