@@ -133,7 +133,8 @@ function _mapreduce_fuse!(f, op, initop, dims::Dims{N}, arrays::Tuple{Vararg{Dev
             pad(map(a -> Int32(dtypecode(eltype(a))), arrays), SB_MAX_OPS, Int32(0)),
             pad(map(a -> Int32(a.op === conj || a.op === adjoint), arrays), SB_MAX_OPS, Int32(0)),     # mapreduce.jl:276-278
             length(toks), pad(Tuple(toks), SB_MAX_TOKENS, SbTok(0, 0, 0, 0)), opcode(op), ic, real(β), imag(β))
-        rc = ccall((:sb_mapreduce, LIB), Cint, (Ptr{Cvoid}, Ref{SbDesc}), ctx(), desc)
+        rc = (ALLREDUCE[] && op !== nothing) ? ccall((:sb_mapreduce_allreduce, LIB), Cint, (Ptr{Cvoid}, Ref{SbDesc}), ctx(), desc) :
+             ccall((:sb_mapreduce, LIB), Cint, (Ptr{Cvoid}, Ref{SbDesc}), ctx(), desc)
         rc == 0 && return arrays[1]
         rc == -2 && throw(DimensionMismatch(unsafe_string(ccall((:sb_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx()))))
         rc == -3 && throw(Unsupported())
@@ -148,5 +149,18 @@ function _mapreduce_fuse!(f, op, initop, dims::Dims{N}, arrays::Tuple{Vararg{Dev
         return arrays[1]
     end
 end
+
+# ---- reductions across GPUs (one Julia process per GPU) -------------------------------------------------------
+# GPU analog of `threadedout` + serial fold (reference src/mapreduce.jl:153-170).  `allgather` is any function that
+# returns the vector of every rank's 64-byte handle in rank order (MPI.Allgather, Distributed.jl, ...).
+function attach_peers!(rank::Integer, world::Integer, allgather)
+    h = Vector{UInt8}(undef, 64)
+    ccall((:sb_peer_export, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), ctx(), h) == 0 || error("sb_peer_export")
+    all = reduce(vcat, allgather(h))
+    ccall((:sb_peer_attach, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), ctx(), rank, world, all) == 0 || error("sb_peer_attach")
+end
+const ALLREDUCE = Ref(false)   # `with_allreduce() do ... end`: reductions inside combine the partials of all ranks
+with_allreduce(f) = (ALLREDUCE[] = true; try f() finally ALLREDUCE[] = false end)
+# (inside `_mapreduce_fuse!` above, `sb_mapreduce` becomes `sb_mapreduce_allreduce` when ALLREDUCE[] && op !== nothing)
 
 end # module

@@ -147,3 +147,37 @@ def test_orbit_gpu_tma_store_and_direct_store_agree(monkeypatch):
                 c.assert_close(c.run_gpu("device", engine=eng), exact=True)
             finally:
                 eng.close()
+
+
+def _random_family_case(rng, dt):
+    """random rank, random set of 2..4 dim permutations of one parent (the first view may itself be permuted)"""
+    N = int(rng.integers(2, 5))
+    n = {2: int(rng.choice([64, 96, 128])), 3: int(rng.choice([16, 32])), 4: int(rng.choice([8, 16]))}[N]
+    shape = (n,) * N
+    nviews = int(rng.integers(2, 5))
+    perms = []
+    while len(perms) < nviews:
+        p = tuple(int(x) for x in rng.permutation(N))
+        if p not in perms:
+            perms.append(p)
+        if len(perms) == 1 and N == 2 and nviews > 2:
+            nviews = 2  # only two distinct permutations of two dims
+    a, b = _dense_pair(shape, dt, seed=int(rng.integers(1 << 30)))
+    Av = ViewSpec.dense(1, shape)
+    prog = {2: [A(0), A(1), F("add")], 3: [A(0), A(1), F("add"), A(2), F("add")], 4: P_SUM4}[len(perms)]
+    return Case(f"orbit_random_N{N}_{'_'.join(''.join(map(str, p)) for p in perms)}_{np.dtype(dt).name}", [b, a],
+                [ViewSpec.dense(0, shape)] + [Av.permutedims(p) for p in perms], prog)
+
+
+def test_orbit_random_permutation_families_emulated():
+    """Whatever the planner decides for a random family of aliased views (fused orbits when the generated group has
+    orbits of <= 4 tiles and the output's fastest dim is moved, the generic / TMA kernels otherwise), the emulated
+    kernels must reproduce the oracle bit for bit; the fused path must be hit for a fair share of the draws."""
+    rng = np.random.default_rng(2026)
+    fused = 0
+    for i in range(40):
+        c = _random_family_case(rng, (np.float32, np.float64)[i % 2])
+        plan = c.plan()
+        fused += "orbit" in plan
+        c.assert_close(c.run_emul(), exact=True)
+    assert fused >= 8, fused
