@@ -1363,7 +1363,7 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
         }
     }
     // orders
-    int ident[MAXTD];
+    int ident[MAXTD] = {0};
     for (int i = 0; i < ntd; ++i) ident[i] = i;
     make_order(ident, ntd, tbits, P.order[0]);
     int32_t smem_elems = 0;
