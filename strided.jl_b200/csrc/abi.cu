@@ -645,7 +645,7 @@ template <class AT> __global__ void __launch_bounds__(256) peer_allreduce_kernel
     pdl_launch_dependents();
     pdl_wait(); // the local reduction wrote K.tmp
     const size_t par = (size_t)(K.epoch & 1u) * SB_PEER_MAX_WORLD;
-    if (W <= 2) {
+    if constexpr (W <= 2) {
         // Low-latency path for 4- and 8-byte elements: every 32-bit half travels in ONE 8-byte store together with the
         // epoch ({word, epoch}; 8-byte stores to peer memory are delivered atomically), so the receiver needs no flag,
         // no fence and no barrier: each thread pushes its element to all ranks and then polls its own copies.
@@ -688,8 +688,7 @@ template <class AT> __global__ void __launch_bounds__(256) peer_allreduce_kernel
             x = init_apply<AT>(K.initop, K.init_re, K.init_im, x);
             store_elem<AT, false>(K.out + ooff, K.out_dtype, K.out_conj, red_apply<AT>(K.op, x, tot));
         }
-        return;
-    }
+    } else {
     for (int o = t; o < K.nout; o += 256) {
         union {
             AT v;
@@ -738,6 +737,7 @@ template <class AT> __global__ void __launch_bounds__(256) peer_allreduce_kernel
         x = init_apply<AT>(K.initop, K.init_re, K.init_im, x);
         store_elem<AT, false>(K.out + off, K.out_dtype, K.out_conj, red_apply<AT>(K.op, x, tot));
     }
+    } // (wide elements)
 }
 } // namespace
 

@@ -73,7 +73,7 @@ SB_HD void tma_consume(const MapParams &P, const TmaParams &T, const TmaThread<N
 #pragma unroll
             for (int k = 0; k < NIN; ++k) a[k] = v[k][j];
             const CT r = fn.template eval<NIN>(P.prog, a);
-            if (re_of(r) == (typename traits<CT>::real)1.2345678e-300f) store_elem<CT, true>(ob + P.g_joff[0][j], P.dtype[0], 0, r);
+            if (re_of(r) == (typename traits<CT>::real)1.2345678e-30f) store_elem<CT, true>(ob + P.g_joff[0][j], P.dtype[0], 0, r);
         }
     } else if (tl.full && VEC && P.gvec[0]) {
 #pragma unroll
