@@ -374,7 +374,10 @@ static cudaError_t launch_jit(const void *fn, unsigned grid, size_t smem, cudaSt
     return cudaLaunchKernelExC(&cfg, fn, args);
 }
 
-static int run_desc(sb_ctx *ctx, const sb_desc &desc)
+// `peer` != nullptr: collective call (sb_mapreduce_allreduce).  If the plan is a reduction with a single output tile whose
+// accumulator type equals the output type, the exchange across GPUs is fused into the reduction kernel (*fused = true);
+// otherwise NOTHING is launched (*fused = false) and the caller runs the two-kernel path.
+static int run_desc(sb_ctx *ctx, const sb_desc &desc, const PeerLink *peer = nullptr, bool *fused = nullptr)
 {
     // plan cache: everything but the base pointers (the reference re-plans on every call; config 3 is ~2 us
     // of device work, so planning must not be on the critical path)
@@ -469,6 +472,13 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc)
     for (int k = 0; k < MAXO; ++k) {
         plan.map.base[k] = (unsigned char *)desc.base[plan.base_src[k] < desc.nops ? plan.base_src[k] : 0];
         plan.red.base[k] = plan.map.base[k];
+    }
+    if (peer) {
+        const bool can = plan.kind == PLAN_REDUCE && plan.red.nouttiles == 1 && plan.red.nout_tile <= PEER_MAX_OUT && plan.key.ct != C64 &&
+                         desc.dtype[0] == plan.key.ct && !std::getenv("SB_NO_FUSED_PEER");
+        *fused = can;
+        if (!can) return SB_OK;
+        plan.red.peer = *peer;
     }
     if (plan.kind == PLAN_NOOP) return SB_OK;
     cudaSetDevice(ctx->device);
@@ -623,9 +633,7 @@ extern "C" int sb_mapreduce(sb_ctx *ctx, const sb_desc *desc)
 // fast rank may already push call n+1 while a slow one still folds call n (it cannot be two calls ahead: it needs the
 // slow rank's flag of call n+1 first).
 namespace {
-constexpr size_t PEER_FLAG_STRIDE = 128;
-constexpr size_t PEER_DATA_OFF = SB_PEER_MAX_WORLD * PEER_FLAG_STRIDE;
-constexpr size_t PEER_SLOT = 16;
+static_assert(PEER_MAX_WORLD == SB_PEER_MAX_WORLD && PEER_MAX_OUT == SB_PEER_MAX_OUT, "header and kernels agree on the buffer layout");
 constexpr size_t PEER_BUF_BYTES = PEER_DATA_OFF + 2 * (size_t)SB_PEER_MAX_WORLD * SB_PEER_MAX_OUT * PEER_SLOT;
 
 struct PeerKernelParams {
@@ -816,24 +824,50 @@ extern "C" int sb_mapreduce_allreduce(sb_ctx *ctx, const sb_desc *desc)
     if (d.dtype[0] < SB_F32 || d.dtype[0] > SB_C64) return set_err(ctx, SB_E_INVALID, "bad dtype");
     PeerKernelParams K;
     std::memset(&K, 0, sizeof K);
-    int64_t nout = 1, dense = 1;
+    int64_t nout = 1;
     bool empty = false;
     sb_desc loc = d; // the local reduction into the dense temporary, started from the neutral element
+    // kept dims in ascending |output stride| (the planner's canonical order): the logical output index used on the wire
+    // is the same whether a rank takes the fused or the two-kernel path
+    int kd[SB_MAX_DIMS], nk = 0;
     for (int i = 0; i < d.ndim; ++i) {
         if (d.dims[i] < 0) return set_err(ctx, SB_E_SHAPE, "negative dim");
         if (d.dims[i] == 0) empty = true;
-        const bool kept = d.strides[0][i] != 0 && d.dims[i] != 1;
-        loc.strides[0][i] = kept ? dense : 0;
-        if (kept) {
-            K.kdims[K.nkept] = d.dims[i];
-            K.kstr_bytes[K.nkept] = d.strides[0][i] * (int64_t)dtype_size(d.dtype[0]);
-            K.nkept++;
-            dense *= d.dims[i];
-            nout *= d.dims[i];
-        }
+        loc.strides[0][i] = 0;
+        if (d.strides[0][i] != 0 && d.dims[i] != 1) kd[nk++] = i;
+    }
+    std::stable_sort(kd, kd + nk, [&](int a, int b) {
+        const int64_t sa = d.strides[0][a] < 0 ? -d.strides[0][a] : d.strides[0][a], sb_ = d.strides[0][b] < 0 ? -d.strides[0][b] : d.strides[0][b];
+        return sa < sb_;
+    });
+    for (int q = 0; q < nk; ++q) {
+        const int i = kd[q];
+        loc.strides[0][i] = nout;
+        K.kdims[K.nkept] = d.dims[i];
+        K.kstr_bytes[K.nkept] = d.strides[0][i] * (int64_t)dtype_size(d.dtype[0]);
+        K.nkept++;
+        nout *= d.dims[i];
     }
     if (nout > SB_PEER_MAX_OUT) return set_err(ctx, SB_E_UNSUPPORTED, "sb_mapreduce_allreduce: more than SB_PEER_MAX_OUT outputs");
     cudaSetDevice(ctx->device);
+    PeerLink link;
+    std::memset(&link, 0, sizeof link);
+    link.world = ctx->peer_world;
+    link.rank = ctx->peer_rank;
+    link.epoch = ++ctx->peer_epoch;
+    for (int g = 0; g < ctx->peer_world; ++g) link.buf[g] = (unsigned char *)ctx->peer_buf[g];
+    if (!empty) { // preferred: the exchange fused into the reduction kernel (one launch)
+        bool fused = false;
+        const int rc = run_desc(ctx, d, &link, &fused);
+        if (rc != SB_OK) return rc;
+        if (fused) {
+            if (ctx->sync) {
+                cudaError_t e = cudaStreamSynchronize(ctx->stream);
+                if (e != cudaSuccess) return cuda_fail(ctx, e, "sb_mapreduce_allreduce");
+            }
+            return SB_OK;
+        }
+    }
     const double neutral = d.op == SB_OP_ADD ? 0.0 : d.op == SB_OP_MUL ? 1.0 : d.op == SB_OP_MIN ? (double)INFINITY : -(double)INFINITY;
     if (!empty) {
         loc.base[0] = ctx->peer_tmp;
@@ -854,8 +888,8 @@ extern "C" int sb_mapreduce_allreduce(sb_ctx *ctx, const sb_desc *desc)
     K.local_empty = empty ? 1 : 0;
     K.out_dtype = d.dtype[0];
     K.out_conj = d.conj[0] && (d.dtype[0] == SB_C32 || d.dtype[0] == SB_C64);
-    K.epoch = ++ctx->peer_epoch;
-    for (int g = 0; g < ctx->peer_world; ++g) K.buf[g] = (unsigned char *)ctx->peer_buf[g];
+    K.epoch = link.epoch;
+    for (int g = 0; g < ctx->peer_world; ++g) K.buf[g] = link.buf[g];
     K.tmp = (const unsigned char *)ctx->peer_tmp;
     K.out = (unsigned char *)d.base[0];
     cudaError_t e;

@@ -289,6 +289,21 @@ struct OrbitParams {
     Program prog;
 };
 
+// ---- peer group (reductions across GPUs, include/strided_b200.h sb_peer_*) ------------------------------------
+// Exchange buffer of a rank: 8 flag words 128 bytes apart (wide elements only), then data[parity][rank][PEER_MAX_OUT]
+// in 16-byte slots.  Elements of <= 8 bytes travel as two 8-byte stores {32-bit half, epoch} (see abi.cu).
+constexpr int PEER_MAX_WORLD = 8;
+constexpr int PEER_MAX_OUT = 1024;
+constexpr uint32_t PEER_FLAG_STRIDE = 128;
+constexpr uint32_t PEER_DATA_OFF = PEER_MAX_WORLD * PEER_FLAG_STRIDE;
+constexpr uint32_t PEER_SLOT = 16;
+struct PeerLink {
+    int32_t world, rank; // world <= 1: no exchange
+    uint32_t epoch;
+    int32_t pad_;
+    unsigned char *buf[PEER_MAX_WORLD]; // rank g's exchange buffer as mapped into this process
+};
+
 // ---- reduce plan ------------------------------------------------------------------------------------
 struct ReduceParams {
     int32_t ndim, nops, ntd;
@@ -330,6 +345,7 @@ struct ReduceParams {
     int32_t op;
     int32_t initop;
     double init_re, init_im;
+    PeerLink peer;               // fused exchange of the final values across GPUs (single output tile plans)
     Program prog;
 };
 

@@ -37,6 +37,77 @@ template <class CT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forcein
     }
 }
 
+// ---- fused exchange across GPUs (peer group) ---------------------------------------------------------------
+// The thread that holds the FINAL local value of output `o` (single output tile plans) exchanges it with all ranks
+// before the store: it pushes the value into slot [epoch parity][rank][logical index] of every rank's buffer as two
+// 8-byte stores {32-bit half, epoch} (atomic over NVLink: no flag, fence or barrier), polls its own copies until every
+// rank's halves carry the epoch, and folds them in rank order (bit-identical on all ranks).  Same wire format as the
+// stand-alone peer_allreduce_kernel of abi.cu, so ranks may mix the two paths.
+SB_D bool peer_logical_index(const ReduceParams &P, int o, int &idx)
+{
+    int64_t lin = 0, mul = 1;
+    bool ok = true;
+    int coord[MAXD];
+    for (int d = 0; d < P.nkept; ++d) coord[d] = 0;
+    for (int i = 0; i < P.kept_order.n; ++i) coord[P.tdim[P.kept_order.td[i]]] = field_of(P.kept_order, i, o);
+    for (int d = 0; d < P.nkept; ++d) { // (single output tile: the tile origin is 0)
+        ok = ok && coord[d] < P.dims[d];
+        lin += coord[d] * mul;
+        mul *= P.dims[d];
+    }
+    idx = (int)lin;
+    return ok && lin < PEER_MAX_OUT;
+}
+template <class AT> SB_D AT peer_ll_allreduce(const ReduceParams &P, int o, AT p)
+{
+#if defined(__CUDA_ARCH__)
+    static_assert(sizeof(AT) <= 8, "the low-latency exchange carries 4- and 8-byte elements");
+    int idx;
+    if (!peer_logical_index(P, o, idx)) return p; // padding lane of the output tile: nothing is stored for it
+    union {
+        AT v;
+        uint32_t w[2];
+    } u;
+    u.w[1] = 0u;
+    u.v = p;
+    const uint32_t epoch = P.peer.epoch;
+    const size_t par = (size_t)(epoch & 1u) * PEER_MAX_WORLD;
+    const size_t off = PEER_DATA_OFF + ((par + (size_t)P.peer.rank) * PEER_MAX_OUT + (size_t)idx) * PEER_SLOT;
+    for (int g = 0; g < P.peer.world; ++g) {
+        unsigned char *dst = P.peer.buf[g] + off;
+        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(u.w[0]), "r"(epoch) : "memory");
+        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst + 8), "r"(u.w[1]), "r"(epoch) : "memory");
+    }
+    AT tot = p;
+    const long long t0 = clock64();
+    for (int g = 0; g < P.peer.world; ++g) {
+        const unsigned char *src = P.peer.buf[P.peer.rank] + PEER_DATA_OFF + ((par + (size_t)g) * PEER_MAX_OUT + (size_t)idx) * PEER_SLOT;
+        uint32_t a0, e0, a1, e1;
+        for (;;) {
+            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(a0), "=r"(e0) : "l"(src) : "memory");
+            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(a1), "=r"(e1) : "l"(src + 8) : "memory");
+            if (e0 == epoch && e1 == epoch) break;
+            if (clock64() - t0 > 4000000000LL) __trap(); // a missing peer must not hang the GPU
+        }
+        u.w[0] = a0;
+        u.w[1] = a1;
+        tot = g == 0 ? u.v : red_apply<AT>(P.op, tot, u.v);
+    }
+    return tot;
+#else
+    (void)P;
+    (void)o;
+    return p;
+#endif
+}
+template <class AT> SB_D AT peer_maybe(const ReduceParams &P, int o, AT p)
+{
+    if constexpr (sizeof(AT) <= 8) {
+        if (P.peer.world > 1) return peer_ll_allreduce<AT>(P, o, p);
+    }
+    return p;
+}
+
 // ---- reduce ---------------------------------------------------------------------------------------------
 template <class T> __device__ __forceinline__ T shfl_xor_any(T v, int mask)
 {
@@ -74,6 +145,7 @@ template <class AT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forcein
         if (t == 0) {
             AT q = smem[0];
             for (int w = 1; w < THREADS / 32; ++w) q = red_apply<AT>(P.op, q, smem[w]);
+            if (P.nsplit == 1) q = peer_maybe<AT>(P, 0, q);
             red_finish<AT, UNIFORM>(P, bid, 0, q);
         }
     } else if (P.warp_per_output) {
@@ -82,10 +154,13 @@ template <class AT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forcein
             AT p = red_lane_partial<AT>(P, smem, o, lane);
 #pragma unroll
             for (int m = 16; m >= 1; m >>= 1) p = red_apply<AT>(P.op, p, shfl_xor_any(p, m));
-            if (lane == 0) red_finish<AT, UNIFORM>(P, bid, o, p);
+            if (lane == 0) red_finish<AT, UNIFORM>(P, bid, o, P.nsplit == 1 ? peer_maybe<AT>(P, o, p) : p);
         }
     } else {
-        for (int o = t; o < P.nout_tile; o += THREADS) red_finish<AT, UNIFORM>(P, bid, o, red_thread_partial<AT>(P, smem, o));
+        for (int o = t; o < P.nout_tile; o += THREADS) {
+            const AT p = red_thread_partial<AT>(P, smem, o);
+            red_finish<AT, UNIFORM>(P, bid, o, P.nsplit == 1 ? peer_maybe<AT>(P, o, p) : p);
+        }
     }
     if (P.nsplit > 1) {
         // Fused finalize: the last split-CTA of an output tile to arrive folds that tile's partials in a fixed order
@@ -124,7 +199,7 @@ template <class AT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forcein
                 if (t == 0) {
                     AT q = smem[0];
                     for (int w = 1; w < THREADS / 32; ++w) q = red_apply<AT>(P.op, q, smem[w]);
-                    red_finalize_store<AT, UNIFORM>(P, (int64_t)out_tile, q);
+                    red_finalize_store<AT, UNIFORM>(P, (int64_t)out_tile, peer_maybe<AT>(P, 0, q));
                 }
             } else {
                 for (int o = warp; o < P.nout_tile; o += THREADS / 32) {
@@ -132,7 +207,7 @@ template <class AT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forcein
                     AT p = red_finalize_lane<AT>(P, out_idx, lane);
 #pragma unroll
                     for (int m = 16; m >= 1; m >>= 1) p = red_apply<AT>(P.op, p, shfl_xor_any(p, m));
-                    if (lane == 0) red_finalize_store<AT, UNIFORM>(P, out_idx, p);
+                    if (lane == 0) red_finalize_store<AT, UNIFORM>(P, out_idx, peer_maybe<AT>(P, o, p));
                 }
             }
             if (t == 0) P.counters[out_tile] = 0u; // re-arm for the next launch

@@ -48,7 +48,7 @@ def _check_fused(rank, world, device, loc2, A3, full):
     launches0 = eng.stats()["launches"]
     out = sharded.sharded_mapreduce("abs2", "+", loc2, dims=(1, 2), shard_dim=2)           # 8 outputs, fused by default now
     np.testing.assert_allclose(out.to_numpy().reshape(-1), (A3 ** 2).sum(axis=(1, 2)), rtol=1e-12)
-    assert eng.stats()["launches"] - launches0 == 2, "local reduction + peer exchange kernel"
+    assert eng.stats()["launches"] - launches0 == 1, "ONE launch: the exchange is fused into the reduction kernel"
     unfused = sharded.sharded_mapreduce("abs2", "+", loc2, dims=(1, 2), shard_dim=2, fused=False)
     np.testing.assert_allclose(out.to_numpy(), unfused.to_numpy(), rtol=1e-13)
     s = sharded.sharded_mapreduce("identity", "+", loc2, shard_dim=2)
@@ -70,6 +70,17 @@ def _check_fused(rank, world, device, loc2, A3, full):
     torch.cuda.synchronize()
     eng.set_sync(True)
     np.testing.assert_allclose(acc.item(), 25 * (full ** 2).sum(), rtol=1e-12)
+    # mixed paths: rank 0 takes the two-kernel path (local reduction + stand-alone exchange kernel), the others the
+    # fused one -- same wire format, same results
+    if rank == 0:
+        os.environ["SB_NO_FUSED_PEER"] = "1"
+    launches0 = eng.stats()["launches"]
+    out2 = sharded.sharded_mapreduce("abs2", "+", loc2, dims=(1, 2), shard_dim=2)
+    assert eng.stats()["launches"] - launches0 == (2 if rank == 0 else 1)
+    assert np.array_equal(out2.to_numpy(), out.to_numpy())
+    s2 = sharded.sharded_mapreduce("identity", "+", loc2, shard_dim=2)
+    assert s2 == s
+    os.environ.pop("SB_NO_FUSED_PEER", None)
     eng.peer_detach()
 
 
