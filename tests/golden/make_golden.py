@@ -25,6 +25,9 @@ def main():
         if c.name in pick:
             exact = c.op == 0 and c.parents[c.views[0].parent].dtype.kind != "c" and "lambda3" not in c.name
             todo.append((c, exact))
+    # the alias-fused orbit path (three rotated views of one parent; 16^3 tiles): smallest shape that takes it
+    from test_orbit import orbit_cases  # noqa: E402
+    todo += [(c, True) for c, _ in orbit_cases() if c.name == "orbit_sum3_float32"]
     for c, exact in todo:
         z = c.to_npz(c.expected(), exact)
         np.savez_compressed(os.path.join(HERE, c.name.replace("!", "_") + ".npz"), **z)

@@ -21,3 +21,16 @@ def test_emulated_baseline_configs():
         c.assert_close(c.run_emul(), exact=True)
     c5 = case_c5(8, 96)
     c5.assert_close(c5.run_emul())
+
+
+def test_golden_fixtures_through_the_emulated_kernels():
+    """the committed fixtures (tests/golden/) through the planner + CPU thread-grid emulation of the kernel bodies"""
+    import os
+    from helpers import Case, ROOT
+    gdir = os.path.join(ROOT, "tests", "golden")
+    for f in sorted(os.listdir(gdir)):
+        if not f.endswith(".npz"):
+            continue
+        z = np.load(os.path.join(gdir, f), allow_pickle=False)
+        case = Case.from_npz(z)
+        case.assert_close(case.run_emul(), z["expected"], exact=bool(z["exact"]))

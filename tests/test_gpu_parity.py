@@ -155,3 +155,16 @@ def test_back_to_back_dependent_launches_are_ordered():
     got = bufs[24 % 2].cpu().numpy().reshape(n, n, order="F")
     np.testing.assert_allclose(got, ref, rtol=1e-12, atol=0)
     np.testing.assert_allclose(acc.item(), ref_acc, rtol=1e-10)
+
+
+def test_golden_fixtures_through_the_cuda_path():
+    """tests/golden/*.npz (inputs + expected outputs committed with the script that made them) through the C ABI"""
+    import os
+    from helpers import Case, ROOT
+    gdir = os.path.join(ROOT, "tests", "golden")
+    files = sorted(f for f in os.listdir(gdir) if f.endswith(".npz"))
+    assert len(files) >= 17
+    for f in files:
+        z = np.load(os.path.join(gdir, f), allow_pickle=False)
+        case = Case.from_npz(z)
+        case.assert_close(case.run_gpu("device"), z["expected"], exact=bool(z["exact"]))
