@@ -221,6 +221,20 @@ def edge_cases():
     return out
 
 
+# README.md:85-89 / :133-137: the compute-bound benchmark expression  B .= A .* exp.(-2 .* A) .+ sin.(A .* A)
+# (the same parent captured four times: four identical views, nothing to fuse, one pass over A)
+def readme_compute_bound_cases(n=1000):
+    out = []
+    for dt in (np.float64, np.float32):
+        rng = _rng("readme_exp_sin", np.dtype(dt).name)
+        a, b = randn(rng, n * n, dt), np.zeros(n * n, dt)
+        V = ViewSpec.dense(1, (n, n))
+        prog = [A(0), K(-2), A(1), F("mul"), F("exp"), F("mul"), A(2), A(3), F("mul"), F("sin"), F("add")]
+        out.append(Case(f"readme_exp_sin_{np.dtype(dt).name}", [b, a], [ViewSpec.dense(0, (n, n)), V, V, V, V], prog,
+                        rtol=2e-5 if dt == np.float32 else None))
+    return out
+
+
 def all_cases(scale=1.0):
     """scale < 1 shrinks the big recipes (for the CPU emulator); 1.0 = the reference's sizes."""
     s = scale
@@ -233,4 +247,5 @@ def all_cases(scale=1.0):
     cases += view_cases()
     cases += reduction_shape_cases(4 if s >= 1 else 1)
     cases += edge_cases()
+    cases += readme_compute_bound_cases(max(int(1000 * s), 64))
     return cases
