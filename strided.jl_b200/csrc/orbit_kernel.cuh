@@ -1,11 +1,14 @@
 // orbit_kernel.cuh -- sm_100a kernel: alias-fused strided map (see common.hpp "orbit" and orbit_tile.hpp).
 //
-//   producer warp : per work item (orbit) waits for a free stage, arms its full barrier with ntile * tile_bytes and
-//                   lets lane s issue the cp.async.bulk.tensor of parent block s        (SASS: UTMALDG, SYNCS)
-//   consumer warps: wait on the full barrier; for each output tile of the orbit compute 256*EPT elements from shared
-//                   memory into one of two staging buffers (fence.proxy.async), meet on a named barrier, and thread 0
-//                   issues the TMA store of the tile (cp.async.bulk.tensor ... bulk_group; SASS: UTMASTG) -- it runs
-//                   while the next tile is computed into the other staging buffer; the stage is released per warp.
+//   producer warp : per work item (orbit): waits for a free stage, copies the item record (TMA coordinates, slot table;
+//                   fetched two items ahead) into shared memory, arms the stage's full barrier with ntile * tile_bytes and
+//                   lets lane s issue the cp.async.bulk.tensor of parent block s                (SASS: UTMALDG, SYNCS)
+//   consumer warps: wait on the full barrier; for each output tile of the orbit compute T*EPT elements from shared memory
+//                   into one of K (2..4) staging buffers (fence.proxy.async), meet on a named barrier, and thread 0 issues
+//                   the TMA store of the tile (cp.async.bulk.tensor ... bulk_group; SASS: UTMASTG) -- up to K-1 stores are
+//                   in flight while the next tiles are computed; every consumer thread releases the stage itself.
+//                   (opt-in: 128-bit st.global from the staging buffer instead of the TMA store, two buffers)
+// Every kernel executes griddepcontrol.launch_dependents / griddepcontrol.wait (PDL, common.hpp).
 // Out-of-bounds parts of edge blocks are zero-filled on load and clipped on store by the TMA unit: no masks anywhere.
 #pragma once
 #include "tma_kernel.cuh"
@@ -72,7 +75,7 @@ map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ 
     __shared__ __align__(8) uint64_t full_bar[ORB_MAXSTAGE];
     __shared__ __align__(8) uint64_t empty_bar[ORB_MAXSTAGE];
     __shared__ __align__(16) uint32_t item_smem[ORB_MAXSTAGE][64];
-    // ring (nstage stages of gmax blocks) followed by two staging buffers; TMA needs 128-byte aligned boxes
+    // ring (nstage stages of gmax blocks) followed by the staging buffers; TMA needs 128-byte aligned boxes
     unsigned char *ring = sb_orbit_smem_raw + ((0u - smem_u32(sb_orbit_smem_raw)) & 127u); // (offset form keeps the address space known: LDS/STS)
     const uint32_t ring_u32 = smem_u32(ring);
     constexpr int NT = 1 << LOGT; // consumer threads
