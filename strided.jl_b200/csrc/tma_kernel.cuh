@@ -1,12 +1,12 @@
 // tma_kernel.cuh -- sm_100a kernel: TMA-fed, mbarrier-pipelined strided map (the permutedims / transpose /
 // `(A .+ A') ./ 2` fast path).  SASS evidence: UTMALDG (cp.async.bulk.tensor) + SYNCS (mbarrier).
 //
-// Pipeline (no warp specialisation needed: the math is a few instructions per element):
-//   thread 0 keeps tiles it, it+1, .., it+nstage-2 in flight: for each it issues, per input operand, one
-//   cp.async.bulk.tensor per box into stage (it % nstage), completing on that stage's mbarrier
-//   (expect_tx = stage bytes);  all 256 threads wait on the stage's mbarrier (parity (it / nstage) & 1),
-//   read their EPT elements per operand from shared memory in OUTPUT order (XOR-swizzled addresses), evaluate
-//   f, store with streaming stores;  one __syncthreads per tile hands the stage back to the producer.
+// Pipeline (warp-specialised, see map_tma_kernel below): a producer warp keeps `nstage` tiles in flight -- per tile it
+//   waits for the stage's EMPTY barrier, arms the FULL barrier with the stage's byte count and lets one lane per
+//   (operand, box) issue the cp.async.bulk.tensor; eight consumer warps wait on the FULL barrier, read their EPT elements
+//   per operand from shared memory in OUTPUT order (XOR-swizzled addresses), evaluate f, store with streaming stores and
+//   release the stage (one arrive per warp).  No CTA-wide barrier in the loop.  Every kernel executes
+//   griddepcontrol.launch_dependents / griddepcontrol.wait (PDL, common.hpp).
 #pragma once
 #include "kernels.cuh"
 #include "tma_tile.hpp"
