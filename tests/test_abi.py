@@ -81,3 +81,30 @@ def test_bank_model_padding_is_conflict_free_for_transpose():
     # the staged operand of C2 must be readable/writable without shared-memory bank conflicts
     p = case_c2(512).plan()
     assert p["smem_bytes"] >= p["tile"][0] * p["tile"][1] * 8
+
+
+def test_header_is_plain_c_and_layout_matches_ctypes(tmp_path):
+    """include/strided_b200.h must compile as C99 (a Julia `ccall` / cgo / JNI binding sees C, not C++), and the
+    struct sizes the C compiler computes must be the ones the ctypes mirror (and julia/StridedB200.jl) assume."""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text('#include "strided_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%zu %zu %zu %d %d %d\\n", sizeof(sb_desc), sizeof(sb_tok), sizeof(sb_stats), '
+                   'SB_PEER_MAX_OUT, SB_PEER_MAX_WORLD, SB_IPC_HANDLE_BYTES); return 0; }\n')
+    exe = tmp_path / "t"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert int(out[0]) == C.sizeof(sb.abi.sb_desc) and int(out[1]) == C.sizeof(sb.abi.sb_tok)
+    assert int(out[2]) == C.sizeof(sb.abi.sb_stats)
+    assert (int(out[3]), int(out[4]), int(out[5])) == (sb.abi.SB_PEER_MAX_OUT, sb.abi.SB_PEER_MAX_WORLD, sb.abi.SB_IPC_HANDLE_BYTES)
+
+
+def test_peer_entry_points_reject_bad_arguments_without_a_gpu():
+    lib = sb.abi.load_library()
+    buf = C.create_string_buffer(64)
+    assert lib.sb_peer_export(None, buf) == sb.abi.SB_E_INVALID
+    assert lib.sb_peer_attach(None, 0, 2, buf) == sb.abi.SB_E_INVALID
+    assert lib.sb_peer_detach(None) == sb.abi.SB_OK
+    d = case_c5(8, 16).desc(case_c5(8, 16).fresh())
+    assert lib.sb_mapreduce_allreduce(None, C.byref(d)) == sb.abi.SB_E_INVALID
