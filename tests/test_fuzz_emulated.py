@@ -1,0 +1,188 @@
+"""CPU suite: property-based fuzzing of the planner + kernel bodies (thread-grid emulation) against the NumPy semantic
+oracle.  Random ranks, extents (incl. 1 and awkward primes), per-operand dim permutations, reversed (negative-stride)
+and stepped dims, offsets that break 16-byte alignment, broadcast (zero-stride) inputs, aliased inputs, map and
+reduce mode with random kept/reduced dims and initop flavours.  The emulator runs the SAME tile bodies and planner
+tables the CUDA kernels use, so an indexing bug found here is a bug on the GPU.  Deterministic (derandomized)."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+from helpers import A, F, K, Case, ViewSpec, randn
+
+DTS = (np.float32, np.float64, np.complex64, np.complex128)
+
+PROGS = {
+    1: [([], True), ([K(3), A(0), F("mul")], True), ([A(0), F("abs2")], False), ([A(0), F("neg")], True)],
+    2: [([A(0), A(1), F("add")], True), ([A(0), A(1), F("add"), K(2), F("div")], True), ([A(0), A(1), F("mul")], False),
+        ([K(0.5), A(0), F("mul"), A(1), F("add")], False), ([A(0), A(1), F("sub")], True)],
+    3: [([A(0), A(1), F("add"), A(2), F("add")], True), ([A(0), A(1), F("mul"), A(2), F("sub")], False)],
+}
+
+
+@st.composite
+def problems(draw):
+    n = draw(st.integers(1, 5))
+    dims = tuple(draw(st.sampled_from([1, 2, 3, 4, 5, 7, 8, 9, 13, 16, 17, 24, 32, 33])) for _ in range(n))
+    while int(np.prod(dims)) > 40000:  # keep the emulation fast
+        dims = tuple(max(1, d // 2) for d in dims)
+    dt = draw(st.sampled_from(DTS))
+    nin = draw(st.integers(1, 3))
+    reduce_mode = draw(st.booleans())
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    rng = np.random.default_rng(seed)
+    parents, views = [], []
+
+    def make_view(pidx, allow_bcast):
+        """a random strided view with the problem's dims over a fresh parent: permuted dense layout, optionally stepped,
+        reversed, offset, or broadcast along some dims"""
+        perm = list(rng.permutation(n))
+        steps = [int(rng.choice([1, 1, 1, 2, 3])) for _ in range(n)]
+        bcast = [allow_bcast and dims[d] > 1 and rng.random() < 0.15 for d in range(n)]
+        strides = [0] * n
+        acc = 1
+        for d in perm:  # dim `d` is the next-fastest in the parent
+            if bcast[d]:
+                strides[d] = 0
+                continue
+            strides[d] = acc * steps[d]
+            acc *= dims[d] * steps[d]
+        off0 = int(rng.integers(0, 4))
+        offset = off0
+        for d in range(n):
+            if strides[d] != 0 and dims[d] > 1 and rng.random() < 0.2:  # reversed range
+                offset += (dims[d] - 1) * strides[d]
+                strides[d] = -strides[d]
+        size = acc + off0 + 3
+        return size, ViewSpec(pidx, offset, dims, tuple(strides))
+
+    if reduce_mode:
+        kept = [bool(rng.random() < 0.5) for _ in range(n)]
+        # output: dense over the kept dims (random order), zero stride on reduced dims
+        order = [d for d in rng.permutation(n) if kept[d]]
+        ostr, acc = [0] * n, 1
+        for d in order:
+            ostr[d] = acc
+            acc *= dims[d]
+        rdt = dt
+        parents.append(randn(rng, acc + 2, rdt))
+        views.append(ViewSpec(0, 1, dims, tuple(ostr)))
+        op = int(rng.choice([1, 1, 1, 3, 4])) if np.dtype(dt).kind == "f" else 1
+        initop, init = [(0, 0.0), (1, 0.0), (3, -0.5), (4, 0.25)][int(rng.integers(0, 4))]
+        if op in (3, 4):
+            initop, init = 0, 0.0
+    else:
+        size, v = make_view(0, allow_bcast=False)
+        parents.append(randn(rng, size, dt))
+        views.append(v)
+        op, initop, init = 0, 0, 0.0
+    for k in range(nin):
+        if k > 0 and rng.random() < 0.25:  # an alias of the previous input's parent under another permutation
+            src = views[-1]
+            p = list(rng.permutation(n))
+            if all(dims[p[i]] == dims[i] for i in range(n)):
+                views.append(ViewSpec(src.parent, src.offset, dims, tuple(src.strides[i] for i in p)))
+                continue
+        size, v = make_view(len(parents), allow_bcast=True)
+        parents.append(randn(rng, size, dt))
+        views.append(v)
+    progs = PROGS[nin] if not (reduce_mode and op in (3, 4)) else [([A(0), F("abs")] if nin == 1 else PROGS[nin][0][0], False)]
+    if reduce_mode and op in (3, 4) and nin > 1:
+        op = 1
+    prog, exact_map = progs[int(rng.integers(0, len(progs)))]
+    if reduce_mode and op in (3, 4):
+        prog, exact_map = [A(0), F("abs")], False
+        views, parents = views[:2], parents[:2]
+        # min/max need a real output
+        rdt = np.float32 if dt in (np.float32, np.complex64) else np.float64
+        parents[0] = np.abs(parents[0]).astype(rdt) if np.dtype(dt).kind == "c" else parents[0]
+    name = f"fuzz_n{n}_{'x'.join(map(str, dims))}_{np.dtype(dt).name}_nin{len(views) - 1}_op{op}_i{initop}_s{seed}"
+    rtol = None
+    if reduce_mode:
+        rtol = 5e-4 if dt in (np.float32, np.complex64) else 1e-10
+    exact = (not reduce_mode) and exact_map and np.dtype(dt).kind == "f"
+    return Case(name, parents, views, prog, op=op, initop=initop, init=init, rtol=rtol), exact
+
+
+@settings(max_examples=160, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(problems())
+def test_emulated_kernels_on_random_strided_problems(prob):
+    case, exact = prob
+    want = case.expected()
+    try:
+        got = case.run_emul()
+    except RuntimeError as e:  # the planner may legitimately decline (SB_E_UNSUPPORTED = -3): CPU fallback in the glue
+        if "(-3)" in str(e):
+            return
+        raise
+    case.assert_close(got, want, exact=exact)
+
+
+@st.composite
+def aligned_problems(draw):
+    """TMA-describable operands (dense permuted layouts, 16-byte aligned rows, no offsets), often aliased: exercises
+    the TMA ring planner/consumer and the alias-fused orbit planner/consumer"""
+    n = draw(st.integers(2, 4))
+    if draw(st.booleans()):
+        d = draw(st.sampled_from({2: [32, 64, 96, 128, 260], 3: [16, 24, 32, 40], 4: [8, 16, 20]}[n]))
+        dims = (d,) * n
+    else:
+        dims = tuple(draw(st.sampled_from([8, 16, 24, 32, 48])) for _ in range(n))
+    while int(np.prod(dims)) > 300000:
+        dims = tuple(max(8, d // 2) for d in dims)
+    dt = draw(st.sampled_from((np.float32, np.float64)))
+    nin = draw(st.integers(1, 4))
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    rng = np.random.default_rng(seed)
+    total = int(np.prod(dims))
+    parents = [np.zeros(total, dt)]
+    views = [ViewSpec.dense(0, dims)]
+    for k in range(nin):
+        alias = k > 0 and rng.random() < 0.7
+        pidx = views[-1].parent if alias else len(parents)
+        if not alias:
+            parents.append(randn(rng, total, dt))
+        # a dense column-major parent of SOME permutation of dims, viewed back in problem order
+        p = list(rng.permutation(n))
+        pdims = [dims[i] for i in p]
+        if alias:
+            base = None
+            for v in views[1:]:
+                if v.parent == pidx:
+                    base = v
+            q = list(rng.permutation(n))
+            if not all(dims[q[i]] == dims[i] for i in range(n)):
+                q = list(range(n))
+            views.append(ViewSpec(pidx, 0, dims, tuple(base.strides[i] for i in q)))
+            continue
+        st_, acc = [0] * n, 1
+        for i, d in zip(p, pdims):
+            st_[i] = acc
+            acc *= d
+        views.append(ViewSpec(pidx, 0, dims, tuple(st_)))
+    prog = {1: [[], [K(3), A(0), F("mul")]], 2: [[A(0), A(1), F("add")], [A(0), A(1), F("add"), K(2), F("div")], [A(0), A(1), F("sub")]],
+            3: [[A(0), A(1), F("add"), A(2), F("add")], [A(0), A(1), F("mul"), A(2), F("sub")]],
+            4: [[A(0), A(1), F("add"), A(2), F("add"), A(3), F("add")]]}[nin]
+    prog = prog[int(rng.integers(0, len(prog)))]
+    name = f"fuzzal_{'x'.join(map(str, dims))}_{np.dtype(dt).name}_nin{nin}_s{seed}"
+    return Case(name, parents, views, prog)
+
+
+_SEEN = {"tma": 0, "orbit": 0, "generic": 0}
+
+
+@settings(max_examples=200, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(aligned_problems())
+def test_emulated_tma_and_orbit_paths_on_random_aligned_problems(case):
+    import os
+    os.environ["SB_ORBIT_NIN2"] = "1"  # let two-view alias families take the fused path too
+    try:
+        plan = case.plan()
+        _SEEN["orbit" if "orbit" in plan else "tma" if plan.get("tma") else "generic"] += 1
+        # (multiplications are single-rounding too: everything here is bit-exact)
+        case.assert_close(case.run_emul(), exact=True)
+    finally:
+        os.environ.pop("SB_ORBIT_NIN2", None)
+
+
+def test_fuzz_reached_every_kernel_family():
+    assert _SEEN["tma"] >= 3 and _SEEN["orbit"] >= 5 and _SEEN["generic"] >= 5, _SEEN
