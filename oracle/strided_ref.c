@@ -390,16 +390,32 @@ static void computeblocks(int N, int lo, int M, const int64_t *dims, const int64
     int64_t b[SB_MAX_DIMS], w[SB_MAX_DIMS];
     for (int i = 0; i < N; ++i) b[i] = dims[i];
     const int n = N - lo;
+    /* Deviation (termination only): with NEGATIVE strides the reference's costs are negative (signed `min` at :137,
+     * SURVEY.md appendix E.2), `_lastargmax` can then keep choosing a dim whose block is already 1 and the reference's
+     * `while` loops would not terminate.  Whenever the chosen dim cannot shrink, the largest remaining block is shrunk
+     * instead; identical to the reference in every case where the reference terminates. */
     for (;;) { /* :491-494 */
         if (totalmemoryregion(N, lo, M, b, bytestrides) < 2 * BLOCKMEMORYSIZE) break;
         for (int i = 0; i < n; ++i) w[i] = (b[lo + i] - 1) * costs[lo + i];
         int i = lo + lastargmax(n, w);
+        if (b[i] <= 1) {
+            i = -1;
+            for (int q = lo; q < N; ++q)
+                if (b[q] > 1 && (i < 0 || b[q] >= b[i])) i = q;
+            if (i < 0) break;
+        }
         b[i] = (b[i] + 1) >> 1;
     }
     for (;;) { /* :495-498 */
         if (totalmemoryregion(N, lo, M, b, bytestrides) <= BLOCKMEMORYSIZE) break;
         for (int i = 0; i < n; ++i) w[i] = (b[lo + i] - 1) * costs[lo + i];
         int i = lo + lastargmax(n, w);
+        if (b[i] <= 1) {
+            i = -1;
+            for (int q = lo; q < N; ++q)
+                if (b[q] > 1 && (i < 0 || b[q] >= b[i])) i = q;
+            if (i < 0) break;
+        }
         b[i] -= 1;
     }
     for (int i = lo; i < N; ++i) blocks[i] = b[i];
