@@ -1597,7 +1597,8 @@ int plan_reduce(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &
     // at least 4 tile steps (>= 32 KB of input) per split: tiny reductions are latency-bound, more partials only
     // lengthen the final fold
     if (P.nouttiles < target) nsplit = std::min<int64_t>(std::max<int64_t>(1, P.nrsteps / 4), (target + P.nouttiles - 1) / P.nouttiles);
-    P.steps_per_split = (P.nrsteps + nsplit - 1) / nsplit;
+    if (nsplit < 1) nsplit = 1;
+    P.steps_per_split = std::max<int64_t>(1, (P.nrsteps + nsplit - 1) / nsplit);
     nsplit = (P.nrsteps + P.steps_per_split - 1) / P.steps_per_split;
     if (nsplit > 0x7fffffff) { err = "too many splits"; return SB_E_UNSUPPORTED; }
     P.nsplit = (int32_t)nsplit;
@@ -1673,6 +1674,16 @@ int build_plan(const sb_desc &d, const DeviceInfo &dev, Plan &plan, std::string 
         plan.kind = PLAN_NOOP;
         plan.family = "noop";
         return SB_OK;
+    }
+    // an index space that cannot exist in 180 GB of HBM is rejected here, before any product of extents can overflow
+    // (the planners below multiply tile counts in int64)
+    {
+        long double total = 1.0L;
+        for (int i = 0; i < c.ndim; ++i) total *= (long double)c.dims[i];
+        if (total > 281474976710656.0L) { // 2^48 elements
+            err = "index space larger than 2^48 elements";
+            return SB_E_UNSUPPORTED;
+        }
     }
     if (c.op == OP_NONE) return plan_map(c, dev, plan, err);
     return plan_reduce(c, dev, plan, err);
