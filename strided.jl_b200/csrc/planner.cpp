@@ -139,6 +139,7 @@ int canonicalise(const sb_desc &d, Canon &c, bool &noop, std::string &err)
     for (int i = 0; i < d.ndim; ++i)
         if (d.dims[i] < 0) { err = "negative dim"; return SB_E_SHAPE; }
 
+    int opsel[MAXO] = {0, 1, 2, 3, 4, 5, 6, 7}; // canonical operand -> descriptor operand (identical inputs are merged below)
     c.nops = d.nops;
     c.op = d.op;
     c.initop = (d.op == SB_OP_NONE) ? (int)INIT_NONE : d.initop;
@@ -160,6 +161,40 @@ int canonicalise(const sb_desc &d, Canon &c, bool &noop, std::string &err)
     int depth = 0;
     int rc = check_program(c, err, depth);
     if (rc != SB_OK) return rc;
+    // Identical input views (same base, eltype, conj flag and strides) are ONE operand: the broadcast front end captures
+    // every occurrence of an array separately (`A .* exp.(-2 .* A) .+ sin.(A .* A)` arrives with four copies of A,
+    // capturestridedargs, src/broadcast.jl:41-46); loading it once is free and keeps such trees inside SB_MAX_OPS.
+    {
+        int remap[MAXO], keep[MAXO], nk = 1;
+        keep[0] = 0;
+        for (int k = 1; k < c.nops; ++k) {
+            int same = -1;
+            for (int q = 1; q < nk && same < 0; ++q) {
+                const int j = keep[q];
+                bool eq = c.base[j] == c.base[k] && c.dtype[j] == c.dtype[k] && c.conj[j] == c.conj[k];
+                for (int i = 0; i < d.ndim && eq; ++i)
+                    if (d.dims[i] != 1 && d.strides[j][i] != d.strides[k][i]) eq = false;
+                if (eq) same = q;
+            }
+            if (same >= 0) remap[k] = same;
+            else {
+                remap[k] = nk;
+                keep[nk++] = k;
+            }
+        }
+        if (nk < c.nops) {
+            for (int i = 0; i < c.ntok; ++i)
+                if (c.tok[i].kind == TOK_ARG) c.tok[i].a = remap[c.tok[i].a + 1] - 1;
+            for (int q = 1; q < nk; ++q) {
+                c.base[q] = c.base[keep[q]];
+                c.dtype[q] = c.dtype[keep[q]];
+                c.conj[q] = c.conj[keep[q]];
+                c.src[q] = keep[q];
+            }
+            c.nops = nk;
+        }
+        for (int q = 0; q < MAXO; ++q) opsel[q] = q < nk ? keep[q] : q;
+    }
 
     // compute type: promote inputs and typed constants (Julia promotes per node; see DESIGN.md "compute type")
     bool cplx = false, dbl = false;
@@ -190,7 +225,7 @@ int canonicalise(const sb_desc &d, Canon &c, bool &noop, std::string &err)
     for (int i = 0; i < d.ndim; ++i) {
         if (d.dims[i] == 1) continue;
         c.dims[n] = d.dims[i];
-        for (int k = 0; k < c.nops; ++k) c.strides[k][n] = d.strides[k][i];
+        for (int k = 0; k < c.nops; ++k) c.strides[k][n] = d.strides[opsel[k]][i];
         ++n;
     }
     if (n == 0) { // a single element
