@@ -167,6 +167,7 @@ template <class R> SB_HD cx<R> call1(int fn, cx<R> x)
     }
     case FN_EXP: {
         R e = m_exp(x.re);
+        if (x.im == (R)0) return cx<R>{e, x.im}; // Julia's exp(::Complex): a zero imaginary part stays zero (exp(x) may be Inf)
         return cx<R>{e * m_cos(x.im), e * m_sin(x.im)};
     }
     case FN_LOG: return cx<R>{m_log(m_hypot(x.re, x.im)), m_atan2(x.im, x.re)};
