@@ -822,16 +822,22 @@ int gf2_rank(const uint32_t *v, int n)
     return r;
 }
 
-// Fills plan.orbit* when every input is a dim-permuted view of one parent and the output's fastest dim is moved
-// by at least one of the permutations (the transposing case).  `prog` is the matched recipe of the map plan.
-bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
+// ---- geometry of an alias family --------------------------------------------------------------------------------
+struct OrbitGeom {
+    int n = 0, nin = 0, esz = 0;
+    int pord[MAXD] = {0};             // parent position -> canonical dim (input 1's strides ascending)
+    int q[ORB_MAXIN + 1][MAXD] = {{0}}; // q[k][d]: parent position of canonical dim d under input k
+    bool moved[MAXD] = {false};       // dim d sits at different parent positions under different views
+    int nmoved = 0;
+    int tb[MAXD] = {0};               // log2 tile extent per canonical dim
+    int ebits = 0;                    // log2 elements per tile
+};
+
+// Is every input a dim-permuted, TMA-describable view of ONE parent, the output TMA-storable, and the output's fastest
+// dim moved by at least one of the permutations (the transposing case)?  Fills pord / q / moved.
+bool orbit_family(const Canon &c, OrbitGeom &G)
 {
-    if (std::getenv("SB_NO_ORBIT")) return false;
-    const int n = c.ndim, nin = c.nops - 1, esz = dtype_size(c.ct);
-    // Two aliased views (A and A'): the TMA ring kernel (two loads through L2, alias-aware tile order) measures
-    // 43.7 us on config 2 against 44.8-46 us here (profiles/r01_v9_orbit_tma_vs_lsu_breakdown.txt) -- both are bound by
-    // the ~20 B/clk/SM the TMA unit moves -- so the fused path is taken from three views on, where it wins 3x.
-    if (nin == 2 && !std::getenv("SB_ORBIT_NIN2")) return false;
+    const int n = G.n = c.ndim, nin = G.nin = c.nops - 1, esz = G.esz = dtype_size(c.ct);
     if (c.op != OP_NONE || nin < 2 || nin > ORB_MAXIN || n < 2 || n > TMA_MAXRANK) return false;
     if (c.ct != F32 && c.ct != F64) return false;
     for (int k = 0; k <= nin; ++k)
@@ -839,104 +845,96 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
     for (int k = 2; k <= nin; ++k)
         if (c.base[k] != c.base[1]) return false;
     if (c.base[0] == c.base[1]) return false;
-    // parent dim order = input 1's strides ascending
-    int pord[MAXD];
     for (int d = 0; d < n; ++d) {
-        pord[d] = d;
+        G.pord[d] = d;
         if (c.strides[1][d] <= 0 || c.strides[0][d] <= 0 || c.dims[d] >= ((int64_t)1 << 31)) return false;
     }
-    std::stable_sort(pord, pord + n, [&](int a, int b) { return c.strides[1][a] < c.strides[1][b]; });
-    if (c.strides[1][pord[0]] != 1 || c.strides[0][0] != 1) return false;
+    std::stable_sort(G.pord, G.pord + n, [&](int a, int b) { return c.strides[1][a] < c.strides[1][b]; });
+    if (c.strides[1][G.pord[0]] != 1 || c.strides[0][0] != 1) return false;
     for (int i = 1; i < n; ++i) {
-        const int64_t sp = c.strides[1][pord[i]], so = c.strides[0][i];
-        if (sp == c.strides[1][pord[i - 1]]) return false;
+        const int64_t sp = c.strides[1][G.pord[i]], so = c.strides[0][i];
+        if (sp == c.strides[1][G.pord[i - 1]]) return false;
         if ((sp * esz) % 16 != 0 || (so * esz) % 16 != 0) return false;
         if (sp * esz >= ((int64_t)1 << 40) || so * esz >= ((int64_t)1 << 40)) return false;
         if (so <= c.strides[0][i - 1]) return false;
     }
-    // q[k][d]: parent position of canonical dim d under input k
-    int q[ORB_MAXIN + 1][MAXD];
     for (int k = 1; k <= nin; ++k) {
         bool used[MAXD] = {false};
         for (int d = 0; d < n; ++d) {
             int hit = -1;
             for (int i = 0; i < n; ++i)
-                if (!used[i] && c.strides[1][pord[i]] == c.strides[k][d] && c.dims[pord[i]] == c.dims[d]) hit = i;
+                if (!used[i] && c.strides[1][G.pord[i]] == c.strides[k][d] && c.dims[G.pord[i]] == c.dims[d]) hit = i;
             if (hit < 0) return false;
             used[hit] = true;
-            q[k][d] = hit;
+            G.q[k][d] = hit;
         }
     }
-    bool moved[MAXD] = {false};
-    int nmoved = 0;
+    G.nmoved = 0;
     for (int d = 0; d < n; ++d) {
+        G.moved[d] = false;
         for (int k = 2; k <= nin; ++k)
-            if (q[k][d] != q[1][d]) moved[d] = true;
-        nmoved += moved[d];
+            if (G.q[k][d] != G.q[1][d]) G.moved[d] = true;
+        G.nmoved += G.moved[d];
     }
-    if (!moved[0] || nmoved < 2) return false;
-    // tile extents: 2^bb along every moved dim (a cube: the tile set must be closed under the permutations), batch
-    // bits along unmoved dims; 256*{4,8,16} elements, <= 16 KB (else <= 32 KB)
-    int cap[MAXD], tb[MAXD] = {0};
-    int capmin = 30;
+    return G.moved[0] && G.nmoved >= 2;
+}
+
+// Tile extents: 2^bb along every moved dim (a cube: the tile set must be closed under the permutations), batch bits along
+// unmoved dims; 1024..4096 elements, <= 16 KB (else <= 32 KB), at least one 32-byte sector per box row.
+bool orbit_tile_bits(const Canon &c, OrbitGeom &G)
+{
+    const int n = G.n, esz = G.esz;
+    int cap[MAXD], capmin = 30;
     for (int d = 0; d < n; ++d) {
         cap[d] = ilog2_ceil(c.dims[d]);
-        if (moved[d]) capmin = std::min(capmin, cap[d]);
+        if (G.moved[d]) capmin = std::min(capmin, cap[d]);
     }
     auto waste_of = [&](int d, int bits) {
         const int64_t t = (int64_t)1 << bits;
         return (double)(((c.dims[d] + t - 1) / t) * t) / (double)c.dims[d];
     };
-    int bbmax = std::min(12 / nmoved, capmin);
+    int bbmax = std::min(12 / G.nmoved, capmin);
     for (;; --bbmax) {
         if (bbmax < 1) return false;
         double w = 1.0;
         for (int d = 0; d < n; ++d)
-            if (moved[d]) w = std::max(w, waste_of(d, bbmax));
+            if (G.moved[d]) w = std::max(w, waste_of(d, bbmax));
         if (w <= 1.2) break;
     }
     int forced_bb = 0;
     if (const char *e = std::getenv("SB_ORBIT_BITS")) forced_bb = std::atoi(e); // tuning knob: log2 cube edge
-    int ebits = 0;
-    bool found = false;
-    for (int pass = 0; pass < 2 && !found; ++pass) {
+    for (int pass = 0; pass < 2; ++pass) {
         const int64_t limit = pass == 0 ? 16384 : 32768;
-        for (int bb = bbmax; bb >= 1 && !found; --bb) {
+        for (int bb = bbmax; bb >= 1; --bb) {
             if (forced_bb > 0 && bb != forced_bb) continue;
-            if (((int64_t)esz << bb) < 32) break; // at least one 32-byte sector per box row
-            int eb = nmoved * bb;
+            if (((int64_t)esz << bb) < 32) break;
+            int eb = G.nmoved * bb;
             if (eb > 12 || ((int64_t)esz << eb) > limit) continue;
             int t2[MAXD] = {0};
             for (int d = 0; d < n; ++d)
-                if (moved[d]) t2[d] = bb;
+                if (G.moved[d]) t2[d] = bb;
             for (int d = 0; d < n && eb < 12; ++d) { // batch bits on unmoved dims (same box position in every view)
-                if (moved[d]) continue;
+                if (G.moved[d]) continue;
                 int add = 0;
                 while (eb + add < 12 && add < cap[d] && ((int64_t)esz << (eb + add + 1)) <= limit && waste_of(d, add + 1) <= 1.2) ++add;
                 t2[d] = add;
                 eb += add;
             }
             if (eb < 10) continue;
-            for (int d = 0; d < n; ++d) tb[d] = t2[d];
-            ebits = eb;
-            found = true;
+            for (int d = 0; d < n; ++d) G.tb[d] = t2[d];
+            G.ebits = eb;
+            return true;
         }
     }
-    if (!found) return false;
-    const int32_t tile_bytes = esz << ebits;
-    // consumer threads: 256.  512 (16 warps) are instantiated too but measure the same (config 4: 30.0 vs 29.7 us,
-    // profiles/r01_v9_orbit_threads_lpt.txt): the tile loop is bound by shared-memory bandwidth and by the SM's memory
-    // request rate (32-byte box rows), not by latency.
-    int logt = 8;
-    if (const char *e = std::getenv("SB_ORBIT_LOGT")) {
-        const int v = std::atoi(e);
-        if ((v == 8 || v == 9) && ebits - v >= 1) logt = v;
-    }
-    const int ept = 1 << (ebits - logt);
-    if (!orbit_instantiated(c.ct, prog.recipe, nin, ept, logt)) return false;
-    const int nthreads = 1 << logt;
+    return false;
+}
 
-    // ---- work items: orbits of the tile grid under  c -> pb_1^-1(pb_k(c)) --------------------------------------
+// Work items: the orbits of the tile grid under  c -> pb_1^-1(pb_k(c))  (pb_k: tile -> parent block of input k), in
+// launch order.  False when an orbit has more than ORB_MAXG tiles or the grid is too small / too large.
+bool orbit_items(const Canon &c, const OrbitGeom &G, std::vector<OrbitItem> &items, int &gmax)
+{
+    const int n = G.n, nin = G.nin, esz = G.esz;
+    const int *tb = G.tb;
     int64_t ntile[MAXD], ntiles = 1;
     for (int d = 0; d < n; ++d) {
         ntile[d] = (c.dims[d] + ((int64_t)1 << tb[d]) - 1) >> tb[d];
@@ -955,9 +953,9 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
         return id;
     };
     int inv1[MAXD]; // parent position -> canonical dim under input 1
-    for (int d = 0; d < n; ++d) inv1[q[1][d]] = d;
+    for (int d = 0; d < n; ++d) inv1[G.q[1][d]] = d;
     auto image = [&](int k, const int64_t *cc, int64_t *nc) { // tile whose input-1 block is input k's block of tile cc
-        for (int d = 0; d < n; ++d) nc[inv1[q[k][d]]] = cc[d];
+        for (int d = 0; d < n; ++d) nc[inv1[G.q[k][d]]] = cc[d];
     };
     // Launch order of the orbit representatives: by cubic SUPER-BLOCKS of 2^sup tiles along every moved dim.  The items
     // in flight at any time then cover, in EVERY view's block family, runs of 2^sup adjacent blocks along that family's
@@ -970,7 +968,7 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
     {
         int64_t nsb[MAXD], nsb_total = 1, sbx[MAXD];
         for (int d = 0; d < n; ++d) {
-            sbx[d] = moved[d] ? ((int64_t)1 << sup) : 1;
+            sbx[d] = G.moved[d] ? ((int64_t)1 << sup) : 1;
             nsb[d] = (ntile[d] + sbx[d] - 1) / sbx[d];
             nsb_total *= nsb[d];
         }
@@ -994,9 +992,9 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
         }
     }
     std::vector<uint8_t> seen((size_t)ntiles, 0);
-    std::vector<OrbitItem> items;
-    int gmax = 1;
     std::vector<int64_t> orb;
+    items.clear();
+    gmax = 1;
     for (const int64_t t0 : visit) {
         if (seen[(size_t)t0]) continue;
         orb.assign(1, t0);
@@ -1027,12 +1025,9 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
                 it.ocrd[m][d] = (int32_t)(cc[d] << tb[d]);
                 it.ooff[m] += (cc[d] << tb[d]) * c.strides[0][d] * esz;
             }
-            for (int i = 0; i < n; ++i) it.pcrd[m][i] = (int32_t)(cc[pord[i]] << tb[pord[i]]);
-            for (int k = 1; k <= nin; ++k) {
-                if (k == 1) {
-                    it.slot[m][0] = (uint8_t)m;
-                    continue;
-                }
+            for (int i = 0; i < n; ++i) it.pcrd[m][i] = (int32_t)(cc[G.pord[i]] << tb[G.pord[i]]);
+            it.slot[m][0] = (uint8_t)m;
+            for (int k = 2; k <= nin; ++k) {
                 image(k, cc, nc);
                 const int64_t id = encode(nc);
                 int s = -1;
@@ -1044,30 +1039,35 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
         }
         items.push_back(it);
     }
-
     // Longest items first: the short orbits (tiles on a diagonal of the tile grid: fewer distinct images) go to the END of
     // the launch order, so that the CTAs that get one item more than the others in the last round get a short one
     // (config 4: 1044 items on 148 CTAs = 7 rounds + 8 items; those 8 are now 1- and 2-tile orbits).
-    std::stable_partition(items.begin(), items.end(), [&](const OrbitItem &it) { return it.ntile == gmax; });
+    const int gm = gmax;
+    std::stable_partition(items.begin(), items.end(), [gm](const OrbitItem &it) { return it.ntile == gm; });
+    return true;
+}
 
-    // ---- thread map x = M u over GF(2): conflict-free shared-memory access for every view ----------------------
-    const int B = ebits, lg = esz == 4 ? 2 : 3;
-    const int L = esz == 4 ? 5 : 4; // lanes served together: a warp of 4-byte or a half-warp of 8-byte accesses
+// Thread map x = M u over GF(2): the columns col[0..B) of M (images of the lane, warp and iteration bits) such that every
+// view's shared-memory access of a warp -- the element-address bits below the bank width, ebit[v][.] -- is conflict free:
+// the lane columns restricted to each view's bank bits must be linearly independent.  Randomised search with a fixed seed.
+bool orbit_thread_map(const OrbitGeom &G, int (*ebit)[16], uint32_t *col)
+{
+    const int n = G.n, nin = G.nin, B = G.ebits;
+    const int L = G.esz == 4 ? 5 : 4; // lanes served together: a warp of 4-byte or a half-warp of 8-byte accesses
     int xshift[MAXD], pshift[MAXD];
     for (int d = 0, s = 0; d < n; ++d) {
         xshift[d] = s;
-        s += tb[d];
+        s += G.tb[d];
     }
     for (int i = 0, s = 0; i < n; ++i) {
         pshift[i] = s;
-        s += tb[pord[i]];
+        s += G.tb[G.pord[i]];
     }
-    int ebit[ORB_MAXIN + 1][16]; // element-address bit of x-bit p under view v (0 = staging/output layout)
-    for (int d = 0; d < n; ++d)
-        for (int r = 0; r < tb[d]; ++r) {
+    for (int d = 0; d < n; ++d) // element-address bit of tile-coordinate bit p under view v (0 = staging / output layout)
+        for (int r = 0; r < G.tb[d]; ++r) {
             const int p = xshift[d] + r;
             ebit[0][p] = p;
-            for (int k = 1; k <= nin; ++k) ebit[k][p] = pshift[q[k][d]] + r;
+            for (int k = 1; k <= nin; ++k) ebit[k][p] = pshift[G.q[k][d]] + r;
         }
     auto restricted = [&](int v, uint32_t m) {
         uint32_t r = 0;
@@ -1075,7 +1075,6 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
             if (((m >> p) & 1u) && ebit[v][p] < L) r ^= 1u << ebit[v][p];
         return r;
     };
-    uint32_t col[16];
     bool ok = false;
     uint64_t rng = 0x9E3779B97F4A7C15ull;
     for (int attempt = 0; attempt < 256 && !ok; ++attempt) {
@@ -1108,7 +1107,43 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
         col[ncol] = 1u << p;
         if (gf2_rank(col, ncol + 1) == ncol + 1) ++ncol;
     }
-    if (ncol != B) return false;
+    return ncol == B;
+}
+
+// Fills plan.orbit* when every input is a dim-permuted view of one parent and the output's fastest dim is moved
+// by at least one of the permutations (the transposing case).  `prog` is the matched recipe of the map plan.
+bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
+{
+    if (std::getenv("SB_NO_ORBIT")) return false;
+    // Two aliased views (A and A'): the TMA ring kernel (two loads through L2, alias-aware tile order) measures
+    // 43.7 us on config 2 against 44.8-46 us here (profiles/r01_v9_orbit_tma_vs_lsu_breakdown.txt) -- both are bound by
+    // the ~20 B/clk/SM the TMA unit moves -- so the fused path is taken from three views on, where it wins 3x.
+    if (c.nops - 1 == 2 && !std::getenv("SB_ORBIT_NIN2")) return false;
+    OrbitGeom G;
+    if (!orbit_family(c, G) || !orbit_tile_bits(c, G)) return false;
+    const int n = G.n, nin = G.nin, esz = G.esz, ebits = G.ebits;
+    const int *tb = G.tb, *pord = G.pord;
+    const int32_t tile_bytes = esz << ebits;
+    // consumer threads: 256.  512 (16 warps) are instantiated too but measure the same (config 4: 30.0 vs 29.7 us,
+    // profiles/r01_v9_orbit_threads_lpt.txt): the tile loop is bound by shared-memory bandwidth and by the SM's memory
+    // request rate (32-byte box rows), not by latency.
+    int logt = 8;
+    if (const char *e = std::getenv("SB_ORBIT_LOGT")) {
+        const int v = std::atoi(e);
+        if ((v == 8 || v == 9) && ebits - v >= 1) logt = v;
+    }
+    const int ept = 1 << (ebits - logt);
+    if (!orbit_instantiated(c.ct, prog.recipe, nin, ept, logt)) return false;
+    const int nthreads = 1 << logt;
+
+    std::vector<OrbitItem> items;
+    int gmax = 1;
+    if (!orbit_items(c, G, items, gmax)) return false;
+
+    const int B = ebits, lg = esz == 4 ? 2 : 3;
+    int ebit[ORB_MAXIN + 1][16];
+    uint32_t col[16];
+    if (!orbit_thread_map(G, ebit, col)) return false;
 
     OrbitParams &O = plan.orbit;
     std::memset(&O, 0, sizeof O);
@@ -1153,6 +1188,11 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
             if (c.dims[d] % ((int64_t)1 << tb[d]) != 0) direct = false;
         O.direct_store = direct ? 1 : 0;
         O.st_groups = tile_bytes / (16 * nthreads);
+        int xshift[MAXD];
+        for (int d = 0, sft = 0; d < n; ++d) {
+            xshift[d] = sft;
+            sft += tb[d];
+        }
         auto xbit_off = [&](int p) -> int64_t { // global byte offset of tile-coordinate bit p (output order)
             for (int d = 0; d < n; ++d)
                 if (p >= xshift[d] && p < xshift[d] + tb[d]) return ((int64_t)1 << (p - xshift[d])) * c.strides[0][d] * esz;
