@@ -47,6 +47,26 @@ def _col(shape):
     return tuple(st)
 
 
+def _kernel(tokens, op, initop, dims, views):
+    """kernel family the planner picks for this call (host-side introspection, sb_plan_describe)"""
+    try:
+        p = sb.plan_describe(sb.make_desc(tokens, op, initop, 0.0, dims, views))
+    except Exception as e:  # pragma: no cover
+        return f"? ({e})"
+    ct = p.get("ct")
+    if p.get("orbit"):
+        o = p["orbit"]
+        return f"map_orbit_kernel<{ct},{p.get('recipe')},EPT={o['ept']}> items {o['items']}, {o['nstage']}-stage TMA ring + TMA store"
+    if p.get("stream"):
+        t = p["stream"]
+        return f"reduce_stream_kernel<{ct},{p.get('recipe')}> grid {t['grid']}, {t['nstage']} x {t['chunk_bytes'] // 1024} KB cp.async.bulk ring"
+    if p.get("tma"):
+        return f"map_tma_kernel<{ct},{p.get('recipe')},EPT={p.get('ept')}> tile {p.get('tile')}, {p['tma']}-stage TMA ring"
+    if p.get("family") == "reduce_tile":
+        return f"reduce_tile_kernel<{ct},{p.get('recipe')},EPT={p.get('ept')}> grid {p.get('grid')}, nsplit {p.get('nsplit')}"
+    return f"{p.get('family')}_kernel<{ct},{p.get('recipe')},EPT={p.get('ept')}> tile {p.get('tile')}"
+
+
 def _entry(name, alg_bytes, ms, peak, **kw):
     g = alg_bytes / (ms * 1e-3) / 1e9
     d = {"config": name, "algorithmic_bytes": alg_bytes, "ms": ms, "GBps": g, "frac_of_peak": g / peak}
@@ -69,7 +89,7 @@ def run_all(eng, peak):
     x, y = torch.randn(n, dtype=torch.float32, device=dev), torch.empty(n, dtype=torch.float32, device=dev)
     X, Y = sb.StridedView(x), sb.StridedView(y)
     ms = _time(lambda i: sb.copy_(Y, X), 20)
-    out.append(_entry("copy f32 2^27 (dense)", 2 * n * 4, ms, peak))
+    out.append(_entry("copy f32 2^27 (dense)", 2 * n * 4, ms, peak, kernel=_kernel([], 0, 0, Y.size, [Y, X])))
     ms = _time(lambda i: y.copy_(x), 20)
     out.append(_entry("torch copy_ f32 2^27 (reference point)", 2 * n * 4, ms, peak))
     del x, y
@@ -82,7 +102,7 @@ def run_all(eng, peak):
     prog = [(1, 0, 3.0, 0.0), A_(0), CALL("mul")]
     views = [[sb.StridedView(Bs[i], (m, m), (1, m)), sb.StridedView(As[i], (m, m), (m, 1))] for i in range(k)]
     ms = _time(lambda i: sb.run_mapreduce(prog, 0, 0, 0.0, (m, m), views[i % k]), 10 * k)
-    out.append(_entry("C1 f64 1000^2 B .= 3 .* A' (rot)", 2 * m * m * 8, ms, peak, sets=k))
+    out.append(_entry("C1 f64 1000^2 B .= 3 .* A' (rot)", 2 * m * m * 8, ms, peak, sets=k, kernel=_kernel(prog, 0, 0, (m, m), views[0])))
     ms = _time(lambda i: sb.run_mapreduce(prog, 0, 0, 0.0, (m, m), views[0]), 200)
     out.append(_entry("C1 f64 1000^2 B .= 3 .* A' (warm, L2-resident)", 2 * m * m * 8, ms, peak))
     del As, Bs, views
@@ -95,7 +115,7 @@ def run_all(eng, peak):
         Bs = [torch.empty(m ** 4, dtype=torch.float64, device=dev) for _ in range(k)]
         pairs = [(sb.StridedView(Bs[i], shape, _col(shape)), sb.StridedView(As[i], shape, _col(shape)).permutedims((3, 2, 1, 0))) for i in range(k)]
         ms = _time(lambda i: sb.copy_(*pairs[i % k]), 20 * k)
-        out.append(_entry(f"C3 f64 {m}^4 permutedims (4,3,2,1) (rot)", 2 * m ** 4 * 8, ms, peak, sets=k))
+        out.append(_entry(f"C3 f64 {m}^4 permutedims (4,3,2,1) (rot)", 2 * m ** 4 * 8, ms, peak, sets=k, kernel=_kernel([], 0, 0, shape, list(pairs[0]))))
         ms = _time(lambda i: sb.copy_(*pairs[0]), 300)
         out.append(_entry(f"C3 f64 {m}^4 permutedims (4,3,2,1) (warm, L2-resident)", 2 * m ** 4 * 8, ms, peak))
         del As, Bs, pairs
@@ -112,7 +132,8 @@ def run_all(eng, peak):
             Av = sb.StridedView(As[i], shape, _col(shape))
             vs.append([sb.StridedView(Bs[i], shape, _col(shape))] + [Av.permutedims(p) for p in ((0, 1, 2, 3), (1, 2, 3, 0), (2, 3, 0, 1), (3, 0, 1, 2))])
         ms = _time(lambda i: sb.run_mapreduce(p4, 0, 0, 0.0, shape, vs[i % k]), 10 * k)
-        out.append(_entry(f"{nm} 4-way permutedims sum (rot)", 2 * m ** 4 * esz, ms, peak, sets=k, operand_bytes=5 * m ** 4 * esz))
+        out.append(_entry(f"{nm} 4-way permutedims sum (rot)", 2 * m ** 4 * esz, ms, peak, sets=k, operand_bytes=5 * m ** 4 * esz,
+                          kernel=_kernel(p4, 0, 0, shape, vs[0])))
         ms = _time(lambda i: sb.run_mapreduce(p4, 0, 0, 0.0, shape, vs[0]), 100)
         out.append(_entry(f"{nm} 4-way permutedims sum (warm)", 2 * m ** 4 * esz, ms, peak))
         del As, Bs, vs
@@ -125,13 +146,13 @@ def run_all(eng, peak):
     O = sb.StridedView(o, (g, kk, kk), (1, 0, 0))
     pa = [A_(0), CALL("abs2")]
     ms = _time(lambda i: sb.run_mapreduce(pa, 1, 0, 0.0, (g, kk, kk), [O, T]), 20)
-    out.append(_entry("C5 f64 8x4096x4096 mapreduce(abs2,+;dims=(2,3)) 1 GPU", g * kk * kk * 8 + 64, ms, peak))
+    out.append(_entry("C5 f64 8x4096x4096 mapreduce(abs2,+;dims=(2,3)) 1 GPU", g * kk * kk * 8 + 64, ms, peak, kernel=_kernel(pa, 1, 0, (g, kk, kk), [O, T])))
     # one dense shard as each of 8 GPUs would hold it: 4096x4096 -> 1 scalar
     sh = torch.randn(kk * kk, dtype=torch.float64, device=dev)
     o1 = torch.zeros(1, dtype=torch.float64, device=dev)
     S = sb.StridedView(sh, (kk, kk), (1, kk))
     O1 = sb.StridedView(o1, (kk, kk), (0, 0))
     ms = _time(lambda i: sb.run_mapreduce(pa, 1, 0, 0.0, (kk, kk), [O1, S]), 50)
-    out.append(_entry("C5 shard f64 4096x4096 -> scalar (per-GPU share of the 8-GPU run)", kk * kk * 8 + 8, ms, peak))
+    out.append(_entry("C5 shard f64 4096x4096 -> scalar (per-GPU share of the 8-GPU run)", kk * kk * 8 + 8, ms, peak, kernel=_kernel(pa, 1, 0, (kk, kk), [O1, S])))
     eng.set_sync(True)
     return out

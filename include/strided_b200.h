@@ -170,7 +170,13 @@ int sb_mapreduce_host(sb_ctx *ctx, const sb_desc *desc);
  *                   OUTPUT has the same number of elements (<= SB_PEER_MAX_OUT) and dtype.  `desc` describes the local
  *                   reduction exactly as for sb_mapreduce (device pointers; a zero-size local slab contributes the
  *                   neutral element).  world == 1 (or not attached): identical to sb_mapreduce.
- * A rank that waits longer than ~2 s for a peer traps (SB_E_CUDA) instead of hanging the GPU. */
+ * The call number that tags the exchanged values lives in device memory and is advanced by the exchanging kernel, so a
+ * collective call may be captured in a CUDA graph and replayed (every replay on every rank, in the same order).
+ * sb_peer_export resets that counter together with the exchange buffer; sb_peer_attach does not touch either, so the
+ * host program must put a barrier between the attach of all ranks and the first collective call.
+ * A rank that waits longer than SB_PEER_TIMEOUT_MS (environment, default 30000) for a peer gives up WITHOUT trapping:
+ * the call (sync mode) or the next sb_sync returns SB_E_CUDA, the result of that call is invalid, the context stays
+ * usable. */
 #define SB_PEER_MAX_OUT 1024
 #define SB_PEER_MAX_WORLD 8
 #define SB_IPC_HANDLE_BYTES 64

@@ -3,6 +3,7 @@
 // There is NO CPU execution path here: without a CUDA device every compute entry point returns
 // SB_E_NODEVICE.  (sb_plan_describe is pure host planning and works anywhere.)
 #include "orbit_kernel.cuh"
+#include "stream_kernel.cuh"
 #include "jit.hpp"
 
 #include <cmath>
@@ -157,7 +158,10 @@ struct sb_ctx {
     std::unordered_map<std::string, CachedPlan> plans;
     // peer group for reductions across GPUs (sb_peer_*): exchange buffers of all ranks, mapped through CUDA IPC
     int peer_rank = 0, peer_world = 1;
-    uint32_t peer_epoch = 0;
+    uint32_t *peer_epoch_dev = nullptr;          // call counter of the collective calls, advanced BY THE KERNELS (graph-replay safe)
+    volatile uint32_t *peer_err_host = nullptr;  // mapped host word: a kernel sets it when a peer did not show up in time
+    uint32_t *peer_err_dev = nullptr;            // ... its device address
+    int64_t peer_timeout_cycles = 0;
     void *peer_local = nullptr;                  // this rank's buffer (cudaMalloc)
     void *peer_buf[SB_PEER_MAX_WORLD] = {nullptr}; // [g] = rank g's buffer as seen from this process
     void *peer_tmp = nullptr;                    // local partial (SB_PEER_MAX_OUT elements of up to 16 bytes)
@@ -184,6 +188,16 @@ static int set_err(sb_ctx *ctx, int code, const std::string &msg)
 static int cuda_fail(sb_ctx *ctx, cudaError_t e, const char *what)
 {
     return set_err(ctx, SB_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// a collective kernel that gave up waiting for a peer raised the mapped flag: report it once (the context stays usable)
+static int peer_check(sb_ctx *ctx)
+{
+    if (ctx->peer_err_host && *ctx->peer_err_host) {
+        *ctx->peer_err_host = 0u;
+        return set_err(ctx, SB_E_CUDA, "sb_mapreduce_allreduce: a peer rank did not arrive within SB_PEER_TIMEOUT_MS; the result of that call is invalid");
+    }
+    return SB_OK;
 }
 
 extern "C" {
@@ -245,6 +259,8 @@ int sb_ctx_destroy(sb_ctx *ctx)
     sb_peer_detach(ctx);
     if (ctx->peer_local) cudaFree(ctx->peer_local);
     if (ctx->peer_tmp) cudaFree(ctx->peer_tmp);
+    if (ctx->peer_epoch_dev) cudaFree(ctx->peer_epoch_dev);
+    if (ctx->peer_err_host) cudaFreeHost((void *)ctx->peer_err_host);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SB_OK;
@@ -275,7 +291,7 @@ int sb_sync(sb_ctx *ctx)
     if (!ctx) return set_err(nullptr, SB_E_INVALID, "null ctx");
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaStreamSynchronize");
-    return SB_OK;
+    return peer_check(ctx);
 }
 
 int sb_malloc(sb_ctx *ctx, size_t bytes, void **out)
@@ -579,7 +595,8 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc, const PeerLink *peer = nul
         // so that partials of one plan can never alias the counters of another
         const size_t counters_bytes = 64 * 1024;
         if (plan.red.nsplit > 1 && (size_t)plan.red.nouttiles * 4 > counters_bytes) return set_err(ctx, SB_E_UNSUPPORTED, "too many output tiles for a split reduction");
-        const size_t scratch_need = plan.red.nsplit > 1 ? counters_bytes + (size_t)plan.scratch_bytes : 0;
+        size_t scratch_need = plan.red.nsplit > 1 ? counters_bytes + (size_t)plan.scratch_bytes : 0;
+        if (plan.stream_ok) scratch_need = std::max(scratch_need, counters_bytes + (size_t)plan.stream_grid * 16);
         if (scratch_need > ctx->scratch_bytes) {
             if (ctx->scratch) {
                 cudaStreamSynchronize(ctx->stream);
@@ -597,6 +614,17 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc, const PeerLink *peer = nul
         plan.red.counters = (uint32_t *)ctx->scratch;
         plan.red.scratch = (unsigned char *)ctx->scratch + counters_bytes;
         cudaError_t e;
+        if (!jk && plan.stream_ok) { // streamed complete reduction: dense inputs, 16-byte aligned at bind time
+            bool aligned = true;
+            for (int q = 1; q <= plan.stream.nin; ++q) aligned = aligned && (((uintptr_t)plan.red.base[q] & 15u) == 0);
+            const StreamEntry *sk = aligned ? find_stream_kernel(plan.key) : nullptr;
+            if (sk) {
+                e = sk->launch(plan.red, plan.stream, (int)plan.stream_grid, (size_t)plan.stream_smem_bytes, ctx->stream);
+                if (e != cudaSuccess) return cuda_fail(ctx, e, "reduce_stream launch");
+                ctx->stats.launches++;
+                return SB_OK;
+            }
+        }
         if (jk) {
             void *args[] = {(void *)&plan.red};
             e = launch_jit((const void *)jk->fn, (unsigned)plan.grid, (size_t)plan.smem_bytes, ctx->stream, args);
@@ -638,7 +666,10 @@ constexpr size_t PEER_BUF_BYTES = PEER_DATA_OFF + 2 * (size_t)SB_PEER_MAX_WORLD 
 
 struct PeerKernelParams {
     int32_t world, rank, nout, op, initop, local_empty, nkept, out_dtype, out_conj;
-    uint32_t epoch;
+    int32_t pad_;
+    uint32_t *epoch_ptr; // device-resident call counter (see PeerLink)
+    uint32_t *err_flag;
+    int64_t timeout_cycles;
     double init_re, init_im;
     int64_t kdims[MAXD], kstr_bytes[MAXD]; // kept dims of the output view and their byte strides
     unsigned char *buf[SB_PEER_MAX_WORLD];
@@ -652,7 +683,10 @@ template <class AT> __global__ void __launch_bounds__(256) peer_allreduce_kernel
     const int t = threadIdx.x;
     pdl_launch_dependents();
     pdl_wait(); // the local reduction wrote K.tmp
-    const size_t par = (size_t)(K.epoch & 1u) * SB_PEER_MAX_WORLD;
+    const uint32_t epoch = __ldcg(K.epoch_ptr) + 1u; // this call's number; advanced on the device (graph replays get fresh epochs)
+    __syncthreads();
+    if (t == 0) __stcg(K.epoch_ptr, epoch);
+    const size_t par = (size_t)(epoch & 1u) * SB_PEER_MAX_WORLD;
     if constexpr (W <= 2) {
         // Low-latency path for 4- and 8-byte elements: every 32-bit half travels in ONE 8-byte store together with the
         // epoch ({word, epoch}; 8-byte stores to peer memory are delivered atomically), so the receiver needs no flag,
@@ -667,8 +701,8 @@ template <class AT> __global__ void __launch_bounds__(256) peer_allreduce_kernel
             const size_t off = PEER_DATA_OFF + ((par + (size_t)K.rank) * SB_PEER_MAX_OUT + (size_t)o) * PEER_SLOT;
             for (int g = 0; g < K.world; ++g) {
                 unsigned char *dst = K.buf[g] + off;
-                asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(u.w[0]), "r"(K.epoch) : "memory");
-                asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst + 8), "r"(u.w[1]), "r"(K.epoch) : "memory");
+                asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(u.w[0]), "r"(epoch) : "memory");
+                asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst + 8), "r"(u.w[1]), "r"(epoch) : "memory");
             }
             AT tot = red_neutral<AT>(K.op);
             const long long t0 = clock64();
@@ -678,8 +712,12 @@ template <class AT> __global__ void __launch_bounds__(256) peer_allreduce_kernel
                 for (;;) {
                     asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(a0), "=r"(e0) : "l"(src) : "memory");
                     asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(a1), "=r"(e1) : "l"(src + 8) : "memory");
-                    if (e0 == K.epoch && e1 == K.epoch) break;
-                    if (clock64() - t0 > 4000000000LL) __trap(); // a missing peer must not hang the GPU
+                    if (e0 == epoch && e1 == epoch) break;
+                    if (clock64() - t0 > K.timeout_cycles) { // a missing peer must not hang the GPU: flag it and go on
+                        *reinterpret_cast<volatile uint32_t *>(K.err_flag) = 1u;
+                        a0 = a1 = 0u;
+                        break;
+                    }
                 }
                 u.w[0] = a0;
                 u.w[1] = a1;
@@ -713,11 +751,14 @@ template <class AT> __global__ void __launch_bounds__(256) peer_allreduce_kernel
     __threadfence_system();
     __syncthreads();
     if (t < K.world) { // thread g: tell rank g that this rank's partial has landed, then wait for rank g's
-        *reinterpret_cast<volatile uint32_t *>(K.buf[t] + PEER_FLAG_STRIDE * (size_t)K.rank) = K.epoch;
+        *reinterpret_cast<volatile uint32_t *>(K.buf[t] + PEER_FLAG_STRIDE * (size_t)K.rank) = epoch;
         volatile uint32_t *f = reinterpret_cast<volatile uint32_t *>(K.buf[K.rank] + PEER_FLAG_STRIDE * (size_t)t);
         const long long t0 = clock64();
-        while ((int32_t)(*f - K.epoch) < 0)
-            if (clock64() - t0 > 4000000000LL) __trap(); // a missing peer must not hang the GPU
+        while ((int32_t)(*f - epoch) < 0)
+            if (clock64() - t0 > K.timeout_cycles) { // a missing peer must not hang the GPU: flag it and go on
+                *reinterpret_cast<volatile uint32_t *>(K.err_flag) = 1u;
+                break;
+            }
     }
     __threadfence_system();
     __syncthreads();
@@ -757,9 +798,25 @@ extern "C" int sb_peer_export(sb_ctx *ctx, unsigned char handle_out[SB_IPC_HANDL
     if (!ctx->peer_local) {
         cudaError_t e = cudaMalloc(&ctx->peer_local, PEER_BUF_BYTES);
         if (e == cudaSuccess) e = cudaMalloc(&ctx->peer_tmp, (size_t)SB_PEER_MAX_OUT * PEER_SLOT);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->peer_epoch_dev, 256);
+        void *hp = nullptr;
+        if (e == cudaSuccess) e = cudaHostAlloc(&hp, 64, cudaHostAllocMapped);
+        if (e == cudaSuccess) {
+            ctx->peer_err_host = (volatile uint32_t *)hp;
+            *ctx->peer_err_host = 0u;
+            e = cudaHostGetDevicePointer((void **)&ctx->peer_err_dev, hp, 0);
+        }
         if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(peer buffer)");
+        // how long a rank waits for its peers before it gives up (flag + SB_E_CUDA, the context stays usable): ranks may
+        // legitimately be seconds apart (first-call plan builds, NVRTC compiles, host stalls) -- NCCL tolerates that too
+        const char *tm = std::getenv("SB_PEER_TIMEOUT_MS");
+        const double ms = tm ? std::atof(tm) : 30000.0;
+        int khz = 0;
+        if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device) != cudaSuccess || khz <= 0) khz = 2000000;
+        ctx->peer_timeout_cycles = (int64_t)(ms * (double)khz);
     }
     cudaError_t e = cudaMemset(ctx->peer_local, 0, PEER_BUF_BYTES);
+    if (e == cudaSuccess) e = cudaMemset(ctx->peer_epoch_dev, 0, 256);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMemset(peer buffer)");
     cudaIpcMemHandle_t h;
@@ -767,7 +824,6 @@ extern "C" int sb_peer_export(sb_ctx *ctx, unsigned char handle_out[SB_IPC_HANDL
     e = cudaIpcGetMemHandle(&h, ctx->peer_local);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaIpcGetMemHandle");
     std::memcpy(handle_out, &h, sizeof h);
-    ctx->peer_epoch = 0;
     return SB_OK;
 }
 
@@ -808,7 +864,9 @@ extern "C" int sb_peer_attach(sb_ctx *ctx, int rank, int world, const unsigned c
     }
     ctx->peer_rank = rank;
     ctx->peer_world = world;
-    ctx->peer_epoch = 0;
+    // (the call counter and the slots are reset TOGETHER, by sb_peer_export only: a re-attach without a fresh export keeps
+    //  counting where the previous group stopped, so stale slots can never match a new epoch)
+    *ctx->peer_err_host = 0u;
     return SB_OK;
 }
 
@@ -854,7 +912,9 @@ extern "C" int sb_mapreduce_allreduce(sb_ctx *ctx, const sb_desc *desc)
     std::memset(&link, 0, sizeof link);
     link.world = ctx->peer_world;
     link.rank = ctx->peer_rank;
-    link.epoch = ++ctx->peer_epoch;
+    link.epoch_ptr = ctx->peer_epoch_dev;
+    link.err_flag = ctx->peer_err_dev;
+    link.timeout_cycles = ctx->peer_timeout_cycles;
     for (int g = 0; g < ctx->peer_world; ++g) link.buf[g] = (unsigned char *)ctx->peer_buf[g];
     if (!empty) { // preferred: the exchange fused into the reduction kernel (one launch)
         bool fused = false;
@@ -864,6 +924,7 @@ extern "C" int sb_mapreduce_allreduce(sb_ctx *ctx, const sb_desc *desc)
             if (ctx->sync) {
                 cudaError_t e = cudaStreamSynchronize(ctx->stream);
                 if (e != cudaSuccess) return cuda_fail(ctx, e, "sb_mapreduce_allreduce");
+                return peer_check(ctx);
             }
             return SB_OK;
         }
@@ -888,7 +949,9 @@ extern "C" int sb_mapreduce_allreduce(sb_ctx *ctx, const sb_desc *desc)
     K.local_empty = empty ? 1 : 0;
     K.out_dtype = d.dtype[0];
     K.out_conj = d.conj[0] && (d.dtype[0] == SB_C32 || d.dtype[0] == SB_C64);
-    K.epoch = link.epoch;
+    K.epoch_ptr = link.epoch_ptr;
+    K.err_flag = link.err_flag;
+    K.timeout_cycles = link.timeout_cycles;
     for (int g = 0; g < ctx->peer_world; ++g) K.buf[g] = link.buf[g];
     K.tmp = (const unsigned char *)ctx->peer_tmp;
     K.out = (unsigned char *)d.base[0];
@@ -904,6 +967,7 @@ extern "C" int sb_mapreduce_allreduce(sb_ctx *ctx, const sb_desc *desc)
     if (ctx->sync) {
         e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) return cuda_fail(ctx, e, "sb_mapreduce_allreduce");
+        return peer_check(ctx);
     }
     return SB_OK;
 }

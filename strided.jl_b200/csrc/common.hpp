@@ -299,8 +299,12 @@ constexpr uint32_t PEER_DATA_OFF = PEER_MAX_WORLD * PEER_FLAG_STRIDE;
 constexpr uint32_t PEER_SLOT = 16;
 struct PeerLink {
     int32_t world, rank; // world <= 1: no exchange
-    uint32_t epoch;
-    int32_t pad_;
+    // The call number ("epoch") lives in DEVICE memory and is advanced by the exchanging kernel itself, so that a CUDA
+    // graph that captured a collective call uses a fresh epoch on every replay (a host-side counter baked into the
+    // kernel parameters would make every replay accept the previous replay's slots).
+    uint32_t *epoch_ptr;
+    uint32_t *err_flag;     // set to 1 (mapped host memory) when a peer did not show up within timeout_cycles
+    int64_t timeout_cycles; // clock64() ticks; the kernel then gives up WITHOUT trapping (the context stays usable)
     unsigned char *buf[PEER_MAX_WORLD]; // rank g's exchange buffer as mapped into this process
 };
 
@@ -347,6 +351,23 @@ struct ReduceParams {
     double init_re, init_im;
     PeerLink peer;               // fused exchange of the final values across GPUs (single output tile plans)
     Program prog;
+};
+
+// ---- streamed complete reduction (reduce_stream_kernel) -----------------------------------------------------------
+// Complete reductions of dense operands (`sum(abs2, A)`, `mapreduce(f, op, A, B)` without `dims`; the per-GPU share of
+// BASELINE config 5) are one long contiguous stream per input: no tile decode is needed at all.  One persistent CTA per
+// SM; a producer thread keeps `nstage` chunks of `chunk_bytes` per input in flight with cp.async.bulk (1-D bulk copy,
+// mbarrier complete_tx) from the first cycle on, eight consumer warps fold the landed chunks out of shared memory with
+// 128-bit loads; CTA partials meet in a fixed order in the last-arriving CTA (one acq_rel atomic per CTA, no fences).
+// GPU analog of the per-task partial slots + serial fold of the reference (src/mapreduce.jl:153-170).
+struct StreamParams {
+    int64_t nelem;       // elements per input (every input is dense, stride 1, the accumulator's type)
+    int64_t vec_bytes;   // bytes per input covered by whole 16-byte vectors (the <16-byte rest is folded by one thread)
+    int64_t nchunks;     // ceil(vec_bytes / chunk_bytes)
+    int32_t nin;
+    int32_t chunk_bytes; // per input per stage (multiple of 16)
+    int32_t nstage;
+    int32_t stage_bytes; // nin * chunk_bytes
 };
 
 // ---- in-tile linear index of element (t, j) -----------------------------------------------------------------

@@ -58,7 +58,22 @@ SB_D bool peer_logical_index(const ReduceParams &P, int o, int &idx)
     idx = (int)lin;
     return ok && lin < PEER_MAX_OUT;
 }
-template <class AT> SB_D AT peer_ll_allreduce(const ReduceParams &P, int o, AT p)
+// Executed by ALL threads of the one CTA that performs the exchange (CTA-uniform call site): the epoch of this
+// collective call = device counter + 1; thread 0 advances the counter once everybody has read it.
+SB_D uint32_t peer_epoch_begin(const PeerLink &L)
+{
+#if defined(__CUDA_ARCH__)
+    if (L.world <= 1) return 0u;
+    const uint32_t e = __ldcg(L.epoch_ptr) + 1u;
+    __syncthreads();
+    if (threadIdx.x == 0) __stcg(L.epoch_ptr, e);
+    return e;
+#else
+    (void)L;
+    return 0u;
+#endif
+}
+template <class AT> SB_D AT peer_ll_allreduce(const ReduceParams &P, int o, AT p, uint32_t epoch)
 {
 #if defined(__CUDA_ARCH__)
     static_assert(sizeof(AT) <= 8, "the low-latency exchange carries 4- and 8-byte elements");
@@ -70,7 +85,6 @@ template <class AT> SB_D AT peer_ll_allreduce(const ReduceParams &P, int o, AT p
     } u;
     u.w[1] = 0u;
     u.v = p;
-    const uint32_t epoch = P.peer.epoch;
     const size_t par = (size_t)(epoch & 1u) * PEER_MAX_WORLD;
     const size_t off = PEER_DATA_OFF + ((par + (size_t)P.peer.rank) * PEER_MAX_OUT + (size_t)idx) * PEER_SLOT;
     for (int g = 0; g < P.peer.world; ++g) {
@@ -87,7 +101,10 @@ template <class AT> SB_D AT peer_ll_allreduce(const ReduceParams &P, int o, AT p
             asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(a0), "=r"(e0) : "l"(src) : "memory");
             asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(a1), "=r"(e1) : "l"(src + 8) : "memory");
             if (e0 == epoch && e1 == epoch) break;
-            if (clock64() - t0 > 4000000000LL) __trap(); // a missing peer must not hang the GPU
+            if (clock64() - t0 > P.peer.timeout_cycles) { // a missing peer must not hang the GPU -- and must not kill the
+                *reinterpret_cast<volatile uint32_t *>(P.peer.err_flag) = 1u; // context either: flag it, the host reports it
+                return p;
+            }
         }
         u.w[0] = a0;
         u.w[1] = a1;
@@ -97,14 +114,16 @@ template <class AT> SB_D AT peer_ll_allreduce(const ReduceParams &P, int o, AT p
 #else
     (void)P;
     (void)o;
+    (void)epoch;
     return p;
 #endif
 }
-template <class AT> SB_D AT peer_maybe(const ReduceParams &P, int o, AT p)
+template <class AT> SB_D AT peer_maybe(const ReduceParams &P, int o, AT p, uint32_t epoch)
 {
     if constexpr (sizeof(AT) <= 8) {
-        if (P.peer.world > 1) return peer_ll_allreduce<AT>(P, o, p);
+        if (P.peer.world > 1) return peer_ll_allreduce<AT>(P, o, p, epoch);
     }
+    (void)epoch;
     return p;
 }
 
@@ -132,6 +151,8 @@ template <class AT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forcein
     pdl_wait(); // (the previous launch may be a reduction re-arming the same arrival counters)
     red_accumulate<AT, RC, NIN, EPT, UNIFORM>(P, bid, t, smem);
     __syncthreads();
+    uint32_t epoch = 0u; // (fused exchange: single output tile plans only, so exactly one CTA exchanges)
+    if (P.nsplit == 1) epoch = peer_epoch_begin(P.peer);
     if (P.warp_per_output && P.nout_tile == 1) {
         // a single output per CTA: all eight warps fold the THREADS*EPT accumulators (layout [0][r]), fixed order
         const int warp = t >> 5, lane = t & 31;
@@ -145,7 +166,7 @@ template <class AT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forcein
         if (t == 0) {
             AT q = smem[0];
             for (int w = 1; w < THREADS / 32; ++w) q = red_apply<AT>(P.op, q, smem[w]);
-            if (P.nsplit == 1) q = peer_maybe<AT>(P, 0, q);
+            if (P.nsplit == 1) q = peer_maybe<AT>(P, 0, q, epoch);
             red_finish<AT, UNIFORM>(P, bid, 0, q);
         }
     } else if (P.warp_per_output) {
@@ -154,12 +175,12 @@ template <class AT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forcein
             AT p = red_lane_partial<AT>(P, smem, o, lane);
 #pragma unroll
             for (int m = 16; m >= 1; m >>= 1) p = red_apply<AT>(P.op, p, shfl_xor_any(p, m));
-            if (lane == 0) red_finish<AT, UNIFORM>(P, bid, o, P.nsplit == 1 ? peer_maybe<AT>(P, o, p) : p);
+            if (lane == 0) red_finish<AT, UNIFORM>(P, bid, o, P.nsplit == 1 ? peer_maybe<AT>(P, o, p, epoch) : p);
         }
     } else {
         for (int o = t; o < P.nout_tile; o += THREADS) {
             const AT p = red_thread_partial<AT>(P, smem, o);
-            red_finish<AT, UNIFORM>(P, bid, o, P.nsplit == 1 ? peer_maybe<AT>(P, o, p) : p);
+            red_finish<AT, UNIFORM>(P, bid, o, P.nsplit == 1 ? peer_maybe<AT>(P, o, p, epoch) : p);
         }
     }
     if (P.nsplit > 1) {
@@ -174,6 +195,7 @@ template <class AT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forcein
         __syncthreads();
         if (sb_is_last) {
             __threadfence();
+            epoch = peer_epoch_begin(P.peer);
             const int warp = t >> 5, lane = t & 31;
             if (P.nout_tile == 1) {
                 // one output (complete reductions; config 5 per GPU): ALL eight warps fold -- thread t takes the splits
@@ -199,7 +221,7 @@ template <class AT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forcein
                 if (t == 0) {
                     AT q = smem[0];
                     for (int w = 1; w < THREADS / 32; ++w) q = red_apply<AT>(P.op, q, smem[w]);
-                    red_finalize_store<AT, UNIFORM>(P, (int64_t)out_tile, peer_maybe<AT>(P, 0, q));
+                    red_finalize_store<AT, UNIFORM>(P, (int64_t)out_tile, peer_maybe<AT>(P, 0, q, epoch));
                 }
             } else {
                 for (int o = warp; o < P.nout_tile; o += THREADS / 32) {
@@ -207,7 +229,7 @@ template <class AT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forcein
                     AT p = red_finalize_lane<AT>(P, out_idx, lane);
 #pragma unroll
                     for (int m = 16; m >= 1; m >>= 1) p = red_apply<AT>(P.op, p, shfl_xor_any(p, m));
-                    if (lane == 0) red_finalize_store<AT, UNIFORM>(P, out_idx, peer_maybe<AT>(P, o, p));
+                    if (lane == 0) red_finalize_store<AT, UNIFORM>(P, out_idx, peer_maybe<AT>(P, o, p, epoch));
                 }
             }
             if (t == 0) P.counters[out_tile] = 0u; // re-arm for the next launch

@@ -144,7 +144,7 @@ map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ 
         orbit_thread_init<NIN>(O, tid, th);
         const uint32_t staging0 = (uint32_t)(S * O.stage_bytes);
         int stage = 0;
-        uint32_t parity = 0, sbuf = 0;
+        uint32_t parity = 0, sbuf = 0, tcount = 0;
         const int K = O.nstaging;
         const int64_t st_t = orbit_store_toff(O, tid);
         pdl_wait(); // the output may still be read or written by the previous kernel
@@ -156,7 +156,9 @@ map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ 
                 const uint32_t slots = *reinterpret_cast<const uint32_t *>(it->slot[m]);
                 const uint32_t sbuf_off = staging0 + sbuf * (uint32_t)O.tile_bytes;
                 if (!(O.debug & 4)) orbit_compute<CT, RC, NIN, EPT>(O, th, ring, (uint32_t)(stage * O.stage_bytes), slots, sbuf_off);
-                if (O.direct_store) {
+                const bool direct_now = O.direct_store == 1 || (O.direct_store == 2 && (tcount & 1u)); // 2: alternate TMA store / st.global
+                ++tcount;
+                if (direct_now) {
                     // two staging buffers: a thread can only reach the writes of tile m+2 (same buffer) through the barrier
                     // of tile m+1, which every thread passes after its own reads of tile m below
                     if (!(O.debug & 16)) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
@@ -166,7 +168,8 @@ map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ 
                     // the NEXT tile is computed into the buffer the store of K-1 tiles ago reads from: that store must have
                     // finished reading before anyone passes the barrier (at most K-2 younger stores may still be pending)
                     if (tid == 0) {
-                        switch (K) {
+                        // (alternating mode: every second tile is a TMA store, so the buffer is reused two stores later)
+                        switch (O.direct_store == 2 ? (K >= 4 ? 3 : 2) : K) {
                         case 2: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
                         case 3: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
                         default: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;

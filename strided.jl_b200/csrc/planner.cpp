@@ -675,8 +675,29 @@ bool tma_instantiated(int ct, int recipe, int nin_t, int ept)
     }
 }
 
+// Cheap pre-check used when the tile size is chosen: could plan_tma accept this problem with 2048-element tiles?
+bool tma_candidate(const Canon &c, int recipe, int nin_t, bool uniform)
+{
+    if (std::getenv("SB_NO_TMA")) return false;
+    const int n = c.ndim, nin = c.nops - 1, esz = dtype_size(c.ct);
+    if (!uniform || nin < 1 || nin > TMA_MAXIN || n > TMA_MAXRANK || n < 2) return false;
+    if (!tma_instantiated(c.ct, recipe, nin_t, 8)) return false;
+    bool transposing = false;
+    for (int k = 1; k <= nin; ++k) {
+        int fast = -1;
+        for (int d = 0; d < n; ++d) {
+            if (c.strides[k][d] <= 0) return false;
+            if (c.strides[k][d] == 1) fast = d;
+            else if ((c.strides[k][d] * esz) % 16 != 0) return false;
+        }
+        if (fast < 0) return false;
+        if (fast != 0) transposing = true; // canonical dim 0 is the output's fastest
+    }
+    return transposing && c.strides[0][0] == 1;
+}
+
 // Fills plan.tma / plan.tma_global when every input tile of the map plan P can be fetched by the TMA unit.
-bool plan_tma(const Canon &c, const MapParams &P, const int *tdim, Plan &plan)
+bool plan_tma(const Canon &c, const MapParams &P, const int *tdim, Plan &plan, const DeviceInfo &dev)
 {
     if (std::getenv("SB_NO_TMA")) return false;
     const int n = c.ndim, nin = c.nops - 1, esz = dtype_size(c.ct);
@@ -779,6 +800,8 @@ bool plan_tma(const Canon &c, const MapParams &P, const int *tdim, Plan &plan)
     if (off > 110 * 1024) return false;
     if (ns < 2) ns = 2;
     if (ns > 4) ns = 4;
+    // one-wave problems (at most two tiles per resident CTA): deeper rings only cost shared memory, i.e. resident CTAs
+    if (P.ntiles <= (int64_t)dev.sm_count * 8) ns = 2;
     if (const char *e = std::getenv("SB_TMA_STAGES")) {
         const int v = std::atoi(e);
         if (v >= 2 && v <= 8) ns = v;
@@ -1186,7 +1209,7 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
         bool direct = tb[0] >= lgV && std::getenv("SB_ORBIT_DIRECT") != nullptr;
         for (int d = 0; d < n; ++d)
             if (c.dims[d] % ((int64_t)1 << tb[d]) != 0) direct = false;
-        O.direct_store = direct ? 1 : 0;
+        O.direct_store = direct ? (std::atoi(std::getenv("SB_ORBIT_DIRECT")) == 2 ? 2 : 1) : 0; // 2: alternate TMA store / st.global per tile (needs 4 staging buffers)
         O.st_groups = tile_bytes / (16 * nthreads);
         int xshift[MAXD];
         for (int d = 0, sft = 0; d < n; ++d) {
@@ -1224,7 +1247,7 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
     // shared memory: `ns` input stages + `ks` output staging buffers.  The TMA unit serves loads and stores in order,
     // so a store queues behind the prefetch of the next stage: with only two staging buffers the consumers stalled on
     // it every tile (profiles/r01_v9_orbit_diag.txt: loads and stores each cost 2 us alone, 10 us together).
-    int ks = O.direct_store ? 2 : 4, ns = (int)((208 * 1024 - ks * (int64_t)tile_bytes) / O.stage_bytes);
+    int ks = O.direct_store == 1 ? 2 : 4, ns = (int)((208 * 1024 - ks * (int64_t)tile_bytes) / O.stage_bytes);
     if (ns < 2) {
         ks = 2;
         ns = (int)((208 * 1024 - 2 * (int64_t)tile_bytes) / O.stage_bytes);
@@ -1352,6 +1375,10 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
         return used_;
     };
     int ept = default_ept(c.ct, P.prog.recipe, template_nin(P.prog.recipe, nin), uniform, needed, elements, dev);
+    // Small transposing problems (BASELINE configs 1 and 3: 1000^2 `3 .* A'`, 32^4 permutedims) keep the 2048-element
+    // tile of the TMA ring kernel instead of shrinking to 1024 elements for the LSU kernel: measured 4.5 -> 3.9 us
+    // (config 3) and 5.9 -> 4.1 us (config 1), profiles/r02_a_exp.txt.
+    if (ept < 8 && !std::getenv("SB_FORCE_EPT") && tma_candidate(c, P.prog.recipe, template_nin(P.prog.recipe, nin), uniform)) ept = 8;
     if (!std::getenv("SB_FORCE_EPT")) { // prefer the largest tile that can be filled without padding waste
         int best = ept, best_left = 1 << 30;
         for (int e = ept; e >= 4; e /= 2) {
@@ -1518,7 +1545,7 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
     if (plan.smem_bytes > 200 * 1024) { err = "staging buffers exceed shared memory"; return SB_E_UNSUPPORTED; }
     plan.grid = std::min<int64_t>(P.ntiles, (int64_t)dev.sm_count * dev.ctas_per_sm);
     if (build_tile_order(c, P, plan.tile_order)) plan.note = "alias-aware tile order";
-    if (plan_tma(c, P, tdim, plan) && P.ntiles <= (1 << 20) && !std::getenv("SB_NO_TILE_DESC")) {
+    if (plan_tma(c, P, tdim, plan, dev) && P.ntiles <= (1 << 20) && !std::getenv("SB_NO_TILE_DESC")) {
         plan.tile_desc.resize((size_t)P.ntiles);
         for (int64_t pos = 0; pos < P.ntiles; ++pos) {
             uint32_t id = plan.tile_order.empty() ? (uint32_t)pos : (uint32_t)plan.tile_order[(size_t)pos];
@@ -1541,6 +1568,56 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
     for (int i = 0; i < n; ++i) plan.elements *= c.dims[i];
     if (uniform && plan_orbit(c, P.prog, plan)) plan.note = "alias-fused orbits";
     return SB_OK;
+}
+
+// mirrored by csrc/kernels_stream.cu
+bool stream_instantiated(int ct, int recipe, int nin_t)
+{
+    if (recipe == RC_INTERP) return nin_t >= 1 && nin_t <= 3;
+    if (recipe == RC_COPY) return nin_t == 1;
+    if (recipe == RC_ABS2) return nin_t == 1 && (ct == F32 || ct == F64);
+    return false;
+}
+
+// Streamed variant (common.hpp "StreamParams"): complete reduction, every input one dense run of the accumulator's type.
+void plan_stream(const Canon &c, const DeviceInfo &dev, bool uniform, Plan &plan)
+{
+    if (std::getenv("SB_NO_STREAM")) return;
+    const int nin = c.nops - 1, esz = dtype_size(c.ct);
+    if (c.nkept != 0 || c.ndim != 1 || !uniform || nin < 1 || nin > 3) return;
+    for (int k = 1; k <= nin; ++k)
+        if (c.strides[k][0] != 1) return;
+    if (!stream_instantiated(plan.key.ct, plan.key.recipe, plan.key.nin)) return;
+    StreamParams &S = plan.stream;
+    std::memset(&S, 0, sizeof S);
+    S.nelem = c.dims[0];
+    if (S.nelem > ((int64_t)1 << 56) / esz) return;
+    S.vec_bytes = (S.nelem * esz) & ~(int64_t)15;
+    if (S.vec_bytes < 64 * 1024) return; // (one or two CTAs of the tiled kernel do as well below that)
+    S.nin = nin;
+    // chunk per input: 32 KB / nin at most (four stages of 32 KB keep ~19 MB in flight over 148 SMs), smaller when the
+    // problem would otherwise leave SMs without a chunk: aim for two chunks per CTA
+    int64_t chunk = 32 * 1024 / (nin == 3 ? 4 : nin);
+    const int64_t want = S.vec_bytes / (2 * (int64_t)dev.sm_count);
+    while (chunk > 4096 && chunk > want) chunk >>= 1;
+    if (const char *e = std::getenv("SB_STREAM_CHUNK")) { // tuning knob (tools/)
+        const int64_t v = std::atoll(e);
+        if (v >= 1024 && v <= 65536 && (v & (v - 1)) == 0) chunk = v;
+    }
+    S.chunk_bytes = (int32_t)chunk;
+    S.stage_bytes = (int32_t)(chunk * nin);
+    S.nchunks = (S.vec_bytes + chunk - 1) / chunk;
+    int ns = (int)(128 * 1024 / S.stage_bytes);
+    ns = std::max(2, std::min(8, ns));
+    if (const char *e = std::getenv("SB_STREAM_STAGES")) {
+        const int v = std::atoi(e);
+        if (v >= 2 && v <= 8) ns = v;
+    }
+    while (ns > 2 && (int64_t)ns * S.stage_bytes > 192 * 1024) --ns;
+    S.nstage = ns;
+    plan.stream_grid = std::min<int64_t>(dev.sm_count, S.nchunks);
+    plan.stream_smem_bytes = (int64_t)ns * S.stage_bytes + 128;
+    plan.stream_ok = true;
 }
 
 int plan_reduce(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err)
@@ -1689,6 +1766,7 @@ int plan_reduce(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &
     plan.elements = 1;
     for (int i = 0; i < n; ++i) plan.elements *= c.dims[i];
     if (plan.grid > 0x7fffffff) { err = "grid too large"; return SB_E_UNSUPPORTED; }
+    plan_stream(c, dev, uniform, plan);
     return SB_OK;
 }
 
@@ -1814,6 +1892,9 @@ std::string describe_plan(const Plan &p)
            << ",\"nsplit\":" << P.nsplit << ",\"steps_per_split\":" << P.steps_per_split
            << ",\"nout_tile\":" << P.nout_tile << ",\"nred_tile\":" << P.nred_tile
            << ",\"warp_per_output\":" << P.warp_per_output << ",\"scratch_bytes\":" << p.scratch_bytes;
+        if (p.stream_ok)
+            os << ",\"stream\":{\"grid\":" << p.stream_grid << ",\"chunk_bytes\":" << p.stream.chunk_bytes << ",\"nstage\":" << p.stream.nstage
+               << ",\"nchunks\":" << p.stream.nchunks << ",\"smem_bytes\":" << p.stream_smem_bytes << "}";
     }
     os << "}";
     return os.str();

@@ -60,6 +60,12 @@ struct Plan {
     std::vector<OrbitItem> orbit_items;  // work items in launch order (uploaded with the plan)
     int64_t orbit_smem_bytes = 0;
     int orbit_tile_b[MAXD] = {0};
+    // streamed variant of a complete reduction over dense inputs (cp.async.bulk ring, one CTA per SM); chosen at bind time
+    // when the input bases are 16-byte aligned
+    bool stream_ok = false;
+    StreamParams stream{};
+    int64_t stream_grid = 0;
+    int64_t stream_smem_bytes = 0;
     std::string note;
 };
 

@@ -1,0 +1,175 @@
+// stream_kernel.cuh -- sm_100a kernel: streamed complete reduction (common.hpp "StreamParams", reduce_stream.hpp).
+//
+//   producer (one elected thread of warp 8): per chunk, waits for the stage's EMPTY barrier, arms the FULL barrier with
+//            the chunk's byte count and issues one cp.async.bulk (1-D bulk copy global -> shared, mbarrier complete_tx)
+//            per input: `nstage` chunks per CTA are in flight from the first cycle on            (SASS: UBLKCP, SYNCS)
+//   consumers (8 warps): wait on the FULL barrier, fold the chunk from shared memory with 128-bit loads into four private
+//            accumulators per thread, release the stage (one arrive per warp)
+//   epilogue: warp butterfly + fixed-order fold of the 8 warp results -> CTA partial -> partials[blockIdx];
+//            ONE atom.add.acq_rel.gpu per CTA on the arrival counter (no __threadfence by 256 threads, no extra
+//            barriers); the last-arriving CTA folds the CTA partials in CTA order, exchanges the value across GPUs when
+//            the call is collective (peer_ll_allreduce) and stores op(initop(out), total).
+// Measured on the per-GPU share of BASELINE config 5 (4096 x 4096 Float64 -> scalar): see DESIGN.md section 4.
+#pragma once
+#include "tma_kernel.cuh"
+#include "reduce_stream.hpp"
+
+namespace sb {
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+constexpr int STREAM_MAXSTAGE = 8;
+constexpr int STREAM_THREADS = THREADS + 32;
+
+template <class AT, int RC, int NIN>
+__global__ void __launch_bounds__(STREAM_THREADS, 1) reduce_stream_kernel(const __grid_constant__ ReduceParams P, const __grid_constant__ StreamParams S)
+{
+    extern __shared__ unsigned char sb_stream_smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[STREAM_MAXSTAGE];
+    __shared__ __align__(8) uint64_t empty_bar[STREAM_MAXSTAGE];
+    __shared__ __align__(16) unsigned char fold_raw[(THREADS / 32) * sizeof(AT)];
+    __shared__ unsigned int is_last;
+    AT *fold = reinterpret_cast<AT *>(fold_raw);
+    unsigned char *ring = sb_stream_smem_raw + ((0u - smem_u32(sb_stream_smem_raw)) & 127u);
+    const uint32_t ring_u32 = smem_u32(ring);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NS = S.nstage;
+    pdl_launch_dependents();
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_wait(); // operands, output, partials and the arrival counter may all be in use by the previous kernel
+    const int64_t nchunks = S.nchunks;
+    const uint32_t grid = gridDim.x;
+    if (warp == THREADS / 32) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t parity = 1; // a fresh barrier passes a wait on parity 1: every stage starts out empty
+            for (int64_t c = blockIdx.x; c < nchunks; c += grid) {
+                mbar_wait(smem_u32(&empty_bar[stage]), parity);
+                const int64_t off = c * (int64_t)S.chunk_bytes;
+                const int64_t left = S.vec_bytes - off;
+                const uint32_t nb = (uint32_t)(left < (int64_t)S.chunk_bytes ? left : (int64_t)S.chunk_bytes);
+                const uint32_t fb = smem_u32(&full_bar[stage]);
+                mbar_expect_tx(fb, nb * (uint32_t)S.nin);
+                const uint32_t dst = ring_u32 + (uint32_t)(stage * S.stage_bytes);
+#pragma unroll
+                for (int k = 0; k < NIN; ++k)
+                    if (k < S.nin) bulk_load_1d(dst + (uint32_t)(k * S.chunk_bytes), P.base[k + 1] + off, nb, fb);
+                if (++stage == NS) {
+                    stage = 0;
+                    parity ^= 1u;
+                }
+            }
+        }
+        return;
+    }
+    // ---------------- consumers ----------------
+    AT acc[STREAM_ACC];
+#pragma unroll
+    for (int q = 0; q < STREAM_ACC; ++q) acc[q] = red_neutral<AT>(P.op);
+    {
+        int stage = 0;
+        uint32_t parity = 0;
+        for (int64_t c = blockIdx.x; c < nchunks; c += grid) {
+            const int64_t left = S.vec_bytes - c * (int64_t)S.chunk_bytes;
+            const int nv = (int)((left < (int64_t)S.chunk_bytes ? left : (int64_t)S.chunk_bytes) >> 4);
+            mbar_wait(smem_u32(&full_bar[stage]), parity);
+            stream_chunk<AT, RC, NIN>(P, S, ring + (size_t)stage * S.stage_bytes, nv, tid, acc);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));
+            if (++stage == NS) {
+                stage = 0;
+                parity ^= 1u;
+            }
+        }
+    }
+    AT p = stream_thread_total<AT>(P, acc);
+    if (blockIdx.x == 0 && tid == 0) p = stream_rest<AT, RC, NIN>(P, S, p);
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) p = red_apply<AT>(P.op, p, shfl_xor_any(p, m));
+    if (lane == 0) fold[warp] = p;
+    asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); // consumers only: the producer warp has retired
+    AT q = red_neutral<AT>(P.op);
+    if (tid == 0) {
+        q = fold[0];
+#pragma unroll
+        for (int w = 1; w < THREADS / 32; ++w) q = red_apply<AT>(P.op, q, fold[w]);
+    }
+    if (grid > 1) {
+        if (tid == 0) {
+            reinterpret_cast<AT *>(P.scratch)[blockIdx.x] = q;
+            unsigned int old;
+            asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(P.counters) : "memory");
+            is_last = (old == grid - 1u) ? 1u : 0u;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+        if (!is_last) return;
+        // the last-arriving CTA: fold the CTA partials in CTA order (thread t takes t, t + 256, ...)
+        const AT *sc = reinterpret_cast<const AT *>(P.scratch);
+        AT r = red_neutral<AT>(P.op);
+        for (uint32_t i = (uint32_t)tid; i < grid; i += THREADS) r = red_apply<AT>(P.op, r, load_partial(sc + i));
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) r = red_apply<AT>(P.op, r, shfl_xor_any(r, m));
+        asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); // fold[] has been read by thread 0 above
+        if (lane == 0) fold[warp] = r;
+        asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+        if (tid == 0) {
+            q = fold[0];
+#pragma unroll
+            for (int w = 1; w < THREADS / 32; ++w) q = red_apply<AT>(P.op, q, fold[w]);
+            *P.counters = 0u; // re-arm for the next launch (stream-ordered: nobody else touches it before)
+        }
+    }
+    if (tid == 0) {
+        if constexpr (sizeof(AT) <= 8) {
+            if (P.peer.world > 1) { // collective call: one value per rank crosses NVLink, folded in rank order
+                const uint32_t epoch = __ldcg(P.peer.epoch_ptr) + 1u;
+                __stcg(P.peer.epoch_ptr, epoch);
+                q = peer_ll_allreduce<AT>(P, 0, q, epoch);
+            }
+        }
+        red_finalize_store<AT, true>(P, 0, q);
+    }
+}
+
+struct StreamEntry {
+    KernelKey key; // (ct, recipe, nin); ept and uniform unused
+    cudaError_t (*launch)(const ReduceParams &, const StreamParams &, int grid, size_t smem, cudaStream_t);
+    const void *func;
+};
+
+template <class AT, int RC, int NIN> struct StreamLaunch {
+    static cudaError_t launch(const ReduceParams &P, const StreamParams &S, int grid, size_t smem, cudaStream_t s)
+    {
+        auto k = reduce_stream_kernel<AT, RC, NIN>;
+        static bool attr_set[64] = {false}; // (the attribute is per function and device, and sticky)
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
+        return launch_pdl(k, grid, STREAM_THREADS, smem, s, P, S);
+    }
+    static const void *func() { return (const void *)reduce_stream_kernel<AT, RC, NIN>; }
+};
+
+#define SB_STREAM_ENTRY(CT, DT, RC, NIN)                                                                             \
+    StreamEntry { KernelKey{DT, RC, NIN, 0, 1}, &StreamLaunch<CT, RC, NIN>::launch, StreamLaunch<CT, RC, NIN>::func() }
+
+const StreamEntry *stream_table(int *n);
+const StreamEntry *find_stream_kernel(const KernelKey &k);
+
+} // namespace sb

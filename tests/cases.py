@@ -136,6 +136,35 @@ def complete_reduction_cases(n=10):
     return out
 
 
+# Complete reductions over DENSE operands large enough for the streamed kernel (csrc/stream_kernel.cuh): ragged tails
+# (element counts that are not a multiple of 16 bytes), 1-3 inputs (`sum(A)`, dot-like `sum(A .* B)`, benchmarks/
+# benchtests.jl:44-68 `benchmark_sum`), every reduction operator, every eltype, a misaligned base (tile kernel at bind
+# time), existing output contents participating (initop === nothing, src/mapreduce.jl:314).
+def stream_reduction_cases(n=70001):
+    out = []
+    for dt in DTYPES:
+        rng = _rng("stream", np.dtype(dt).name)
+        nm = np.dtype(dt).name
+        tol = 2e-4 if dt in (np.float32, np.complex64) else 1e-11
+        x, y, z = (rand(rng, n + 5, dt) - 0.5).astype(dt), (rand(rng, n + 5, dt) - 0.5).astype(dt), (rand(rng, n + 5, dt) + 0.5).astype(dt)
+        O = ViewSpec(0, 0, (n,), (0,))
+        X, Y, Z = ViewSpec(1, 0, (n,), (1,)), ViewSpec(2, 0, (n,), (1,)), ViewSpec(3, 0, (n,), (1,))
+        out.append(Case(f"stream_sum_{nm}", [np.full(1, 3, dt), x], [O, X], P_COPY, op=1, rtol=tol))
+        out.append(Case(f"stream_sum_init0_{nm}", [np.full(1, 3, dt), x], [O, X], P_COPY, op=1, initop=1, rtol=tol))
+        out.append(Case(f"stream_dot_{nm}", [np.zeros(1, dt), x, y], [O, X, Y], [A(0), A(1), F("mul")], op=1, rtol=tol))
+        out.append(Case(f"stream_3in_{nm}", [np.zeros(1, dt), x, y, z], [O, X, Y, Z], [A(0), A(1), F("mul"), A(2), F("div")], op=1, rtol=tol * 50))
+        out.append(Case(f"stream_sum_off1_{nm}", [np.zeros(1, dt), x], [O, ViewSpec(1, 1, (n,), (1,))], P_COPY, op=1, rtol=tol))
+        out.append(Case(f"stream_sum_even_{nm}", [np.zeros(1, dt), x], [ViewSpec(0, 0, (n - 1,), (0,)), ViewSpec(1, 0, (n - 1,), (1,))], P_COPY, op=1, rtol=tol))
+        if np.dtype(dt).kind == "f":
+            out.append(Case(f"stream_abs2_{nm}", [np.zeros(1, dt), x], [O, X], [A(0), F("abs2")], op=1, rtol=tol))
+            out.append(Case(f"stream_max_{nm}", [np.full(1, -9, dt), x], [O, X], P_COPY, op=4))
+            out.append(Case(f"stream_min_{nm}", [np.full(1, 9, dt), x], [O, X], P_COPY, op=3))
+            small = (1 + (rand(rng, 4100 * (8 // np.dtype(dt).itemsize) * 2, dt) - 0.5) * 1e-3).astype(dt)
+            m = small.size
+            out.append(Case(f"stream_prod_{nm}", [np.ones(1, dt), small], [ViewSpec(0, 0, (m,), (0,)), ViewSpec(1, 0, (m,), (1,))], P_COPY, op=2, rtol=tol))
+    return out
+
+
 # othertests.jl:130-190 "@strided macro": stepped ranges, views of adjoints, size-1 broadcast dims, reshape
 def view_cases():
     out = []
@@ -244,6 +273,7 @@ def all_cases(scale=1.0):
     cases += broadcast_cases(10 if s >= 1 else 6)
     cases += mapreduce_cases(10 if s >= 1 else 4, 100 if s >= 1 else 23)
     cases += complete_reduction_cases(10 if s >= 1 else 4)
+    cases += stream_reduction_cases(70001 if s >= 1 else 20011)
     cases += view_cases()
     cases += reduction_shape_cases(4 if s >= 1 else 1)
     cases += edge_cases()

@@ -10,6 +10,7 @@
 #include "../../strided.jl_b200/csrc/planner.hpp"
 #include "../../strided.jl_b200/csrc/tma_tile.hpp"
 #include "../../strided.jl_b200/csrc/orbit_tile.hpp"
+#include "../../strided.jl_b200/csrc/reduce_stream.hpp"
 #include <cstdlib>
 
 #include <cstring>
@@ -223,6 +224,84 @@ template <class AT, int RC, int NIN, int EPT, bool U> static void run_reduce(con
     }
 }
 
+// Streamed complete reduction: the cp.async.bulk chunk copies are emulated (plain copies of the chunk of every input into
+// the stage), the real consumer body runs per thread; warp butterfly, CTA fold, partials and the last-CTA fold follow
+// the kernel's order (csrc/stream_kernel.cuh).
+template <class AT> static AT butterfly(const ReduceParams &P, AT *p)
+{
+    for (int m = 16; m >= 1; m >>= 1) {
+        AT q[32];
+        for (int lane = 0; lane < 32; ++lane) q[lane] = red_apply<AT>(P.op, p[lane], p[lane ^ m]);
+        std::memcpy(p, q, sizeof q);
+    }
+    return p[0];
+}
+template <class AT, int RC, int NIN> static void run_stream(const Plan &plan)
+{
+    const ReduceParams &P = plan.red;
+    const StreamParams &S = plan.stream;
+    const int grid = (int)plan.stream_grid;
+    std::vector<unsigned char> raw((size_t)S.stage_bytes + 64);
+    unsigned char *stage = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(raw.data()) + 15) & ~(uintptr_t)15);
+    std::vector<AT> partials((size_t)grid);
+    using Acc = AT[STREAM_ACC];
+    for (int b = 0; b < grid; ++b) {
+        std::vector<char> accbuf(sizeof(Acc) * THREADS);
+        Acc *acc = reinterpret_cast<Acc *>(accbuf.data());
+        for (int t = 0; t < THREADS; ++t)
+            for (int q = 0; q < STREAM_ACC; ++q) acc[t][q] = red_neutral<AT>(P.op);
+        for (int64_t c = b; c < S.nchunks; c += grid) {
+            const int64_t off = c * (int64_t)S.chunk_bytes;
+            const int64_t left = S.vec_bytes - off;
+            const int64_t nb = left < S.chunk_bytes ? left : S.chunk_bytes;
+            std::memset(stage, 0xCD, (size_t)S.stage_bytes);
+            for (int k = 0; k < S.nin; ++k) std::memcpy(stage + (size_t)k * S.chunk_bytes, P.base[k + 1] + off, (size_t)nb);
+            for (int t = 0; t < THREADS; ++t) stream_chunk<AT, RC, NIN>(P, S, stage, (int)(nb >> 4), t, acc[t]);
+        }
+        AT wres[THREADS / 32];
+        for (int w = 0; w < THREADS / 32; ++w) {
+            AT p[32];
+            for (int lane = 0; lane < 32; ++lane) {
+                const int t = w * 32 + lane;
+                p[lane] = stream_thread_total<AT>(P, acc[t]);
+                if (b == 0 && t == 0) p[lane] = stream_rest<AT, RC, NIN>(P, S, p[lane]);
+            }
+            wres[w] = butterfly<AT>(P, p);
+        }
+        AT q = wres[0];
+        for (int w = 1; w < THREADS / 32; ++w) q = red_apply<AT>(P.op, q, wres[w]);
+        partials[(size_t)b] = q;
+    }
+    AT total = partials[0];
+    if (grid > 1) {
+        AT wres[THREADS / 32];
+        for (int w = 0; w < THREADS / 32; ++w) {
+            AT p[32];
+            for (int lane = 0; lane < 32; ++lane) {
+                AT r = red_neutral<AT>(P.op);
+                for (int i = w * 32 + lane; i < grid; i += THREADS) r = red_apply<AT>(P.op, r, partials[(size_t)i]);
+                p[lane] = r;
+            }
+            wres[w] = butterfly<AT>(P, p);
+        }
+        total = wres[0];
+        for (int w = 1; w < THREADS / 32; ++w) total = red_apply<AT>(P.op, total, wres[w]);
+    }
+    red_finalize_store<AT, true>(P, 0, total);
+}
+template <class AT> static bool stream_dispatch(const Plan &plan)
+{
+    const KernelKey &k = plan.key;
+    if (k.recipe == RC_COPY && k.nin == 1) { run_stream<AT, RC_COPY, 1>(plan); return true; }
+    if constexpr (!traits<AT>::cplx) {
+        if (k.recipe == RC_ABS2 && k.nin == 1) { run_stream<AT, RC_ABS2, 1>(plan); return true; }
+    }
+    if (k.recipe == RC_INTERP && k.nin == 1) { run_stream<AT, RC_INTERP, 1>(plan); return true; }
+    if (k.recipe == RC_INTERP && k.nin == 2) { run_stream<AT, RC_INTERP, 2>(plan); return true; }
+    if (k.recipe == RC_INTERP && k.nin == 3) { run_stream<AT, RC_INTERP, 3>(plan); return true; }
+    return false;
+}
+
 // dispatch over the instantiated tuples (mirror of csrc/kernels_*.cu)
 template <class CT, bool U> static bool map_dispatch_interp(const Plan &plan, int grid)
 {
@@ -324,6 +403,19 @@ extern "C" int emul_mapreduce(const sb_desc *desc, int grid_limit)
     } else {
         std::vector<unsigned char> scratch((size_t)plan.scratch_bytes + 64);
         plan.red.scratch = scratch.data();
+        if (plan.stream_ok && !std::getenv("SB_EMUL_NO_STREAM")) {
+            bool aligned = true;
+            for (int k = 1; k <= plan.stream.nin; ++k) aligned = aligned && ((reinterpret_cast<uintptr_t>(plan.red.base[k]) & 15u) == 0);
+            if (aligned) {
+                switch (plan.key.ct) {
+                case F32: ok = stream_dispatch<float>(plan); break;
+                case F64: ok = stream_dispatch<double>(plan); break;
+                case C32: ok = stream_dispatch<cx<float>>(plan); break;
+                default: ok = stream_dispatch<cx<double>>(plan); break;
+                }
+                if (ok) return SB_OK;
+            }
+        }
         switch (plan.key.ct) {
         case F32: ok = red_dispatch<float, 8>(plan); break;
         case F64: ok = red_dispatch<double, 8>(plan); break;

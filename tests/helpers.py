@@ -207,7 +207,7 @@ def emul_lib():
     so = os.path.join(d, "libsb_emul.so")
     csrc = os.path.join(ROOT, "strided.jl_b200", "csrc")
     srcs = [os.path.join(d, "emul.cpp"), os.path.join(csrc, "planner.cpp")]
-    deps = srcs + [os.path.join(csrc, f) for f in ("common.hpp", "elem.hpp", "functors.hpp", "map_tile.hpp", "reduce_tile.hpp", "planner.hpp", "tma_tile.hpp", "orbit_tile.hpp")]
+    deps = srcs + [os.path.join(csrc, f) for f in ("common.hpp", "elem.hpp", "functors.hpp", "map_tile.hpp", "reduce_tile.hpp", "planner.hpp", "tma_tile.hpp", "orbit_tile.hpp", "reduce_stream.hpp")]
     if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-o", so] + srcs)
     lib = C.CDLL(so)

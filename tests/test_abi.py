@@ -50,10 +50,14 @@ def test_plans_for_baseline_configs():
     assert p["family"] == "map_tile" and p["recipe"] == "add2_mul" and p["ct"] == "f64"
     assert p["tile"] == [64, 32] and p["staged"] == [0, 0, 1] and p["ntiles"] == 63 * 125
     assert p["tile_order"] == 1  # A and A' alias: tiles (I,J),(J,I) are launched side by side
+    assert p["tma"] >= 2  # the TMA ring kernel
     p = case_c1(1000).plan()
     assert p["recipe"] == "scale" and p["staged"] == [0, 1] and p["tile_order"] == 0
-    p = case_c3(32).plan()  # one-wave problem: smaller tiles so that every SM gets work
-    assert p["recipe"] == "copy" and p["dims"] == [32, 32, 32, 32] and p["tile"] == [32, 1, 1, 32] and p["ept"] == 4
+    assert p["tma"] == 2 and p["ept"] == 8  # the permutedims/transpose case goes through the TMA ring at every size
+    p = case_c3(32).plan()  # one-wave problem: 2048-element tiles of the TMA ring kernel, two stages
+    assert p["recipe"] == "copy" and p["dims"] == [32, 32, 32, 32] and p["tile"] == [32, 2, 1, 32] and p["ept"] == 8 and p["tma"] == 2
+    p = case_c5(1, 4096).plan()  # per-GPU share of config 5: one dense run -> streamed complete reduction
+    assert p["dims"] == [16777216] and p["stream"]["grid"] == 148 and p["stream"]["chunk_bytes"] == 32768 and p["stream"]["nstage"] == 4
     p = case_c4(64).plan()
     assert p["recipe"] == "sum4" and p["ept"] == 16 and p["tile"] == [8, 8, 8, 8] and p["staged"] == [0, 0, 1, 1, 1]
     assert p["tile_order"] == 1

@@ -70,6 +70,33 @@ def _check_fused(rank, world, device, loc2, A3, full):
     torch.cuda.synchronize()
     eng.set_sync(True)
     np.testing.assert_allclose(acc.item(), 25 * (full ** 2).sum(), rtol=1e-12)
+    # a collective call captured in a CUDA graph and REPLAYED with different data: the call number lives in device
+    # memory and is advanced by the kernel, so every replay gets fresh epochs (a host-side counter baked into the kernel
+    # parameters would let a rank accept the previous replay's slots)
+    x = torch.zeros(4096, dtype=torch.float64, device=device)
+    tot = torch.zeros(1, dtype=torch.float64, device=device)
+    X, T = sb.StridedView(x, (4096,), (1,)), sb.StridedView(tot, (4096,), (0,))
+    ident = [(0, 0, 0.0, 0.0)]
+    eng.set_sync(False)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        eng.set_stream(side.cuda_stream)
+        sb.run_mapreduce(ident, 1, 1, 0.0, (4096,), [T, X], engine=eng, allreduce=True)  # plan + buffers before capture
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(3):  # three collective calls per replay: both slot parities are exercised
+                sb.run_mapreduce(ident, 1, 1, 0.0, (4096,), [T, X], engine=eng, allreduce=True)
+        for it in range(6):
+            x.fill_(float(it + 1) * (rank + 1))
+            if it % 2 == rank % 2:
+                torch.cuda._sleep(20_000_000)  # skew the ranks (~10 ms): the fast one must wait, not take stale data
+            graph.replay()
+            torch.cuda.synchronize()
+            want = 4096.0 * (it + 1) * sum(r + 1 for r in range(world))
+            assert tot.item() == want, (it, tot.item(), want)
+        del graph
+    eng.set_sync(True)
     # mixed paths: rank 0 takes the two-kernel path (local reduction + stand-alone exchange kernel), the others the
     # fused one -- same wire format, same results
     if rank == 0:
