@@ -152,7 +152,11 @@ int sb_mapreduce(sb_ctx *ctx, const sb_desc *desc);
 
 /* Same call for HOST-resident operands (plain Julia `Array` parents): stages every distinct parent
  * range to the device once (aliased views share one copy), runs sb_mapreduce, copies the output
- * range back.  This is the end-to-end entry `bench.py` times as "e2e". */
+ * range back.  This is the end-to-end entry `bench.py` times as "e2e".
+ * Zero-copy mode: a SYNCHRONOUS call (sb_ctx_set_sync != 0) whose operands are all pinned / registered host memory
+ * (cudaHostAlloc, cudaHostRegister) and whose inputs would cross the host link exactly once (a map without broadcast
+ * re-reads; aliased permuted views of one parent are fetched once by the orbit kernel) is served by ONE kernel that
+ * reads and writes host memory directly, so both directions of the link overlap.  SB_HOST_ZERO_COPY=0 disables it. */
 int sb_mapreduce_host(sb_ctx *ctx, const sb_desc *desc);
 
 /* ---- reductions across GPUs (one process per GPU) --------------------------------------------------
@@ -198,6 +202,7 @@ typedef struct sb_stats {
     uint64_t plans_built;
     uint64_t plans_cached;
     uint64_t jit_launches; /* launches of NVRTC-specialised kernels (subset of `launches`) */
+    uint64_t zero_copy_calls; /* sb_mapreduce_host calls served without staging (kernel reads/writes pinned host memory) */
 } sb_stats;
 int sb_get_stats(sb_ctx *ctx, sb_stats *out);
 int sb_reset_stats(sb_ctx *ctx);

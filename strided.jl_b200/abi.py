@@ -53,7 +53,8 @@ class sb_desc(C.Structure):
 
 class sb_stats(C.Structure):
     _fields_ = [("launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("plans_built", C.c_uint64), ("plans_cached", C.c_uint64), ("jit_launches", C.c_uint64)]
+                ("plans_built", C.c_uint64), ("plans_cached", C.c_uint64), ("jit_launches", C.c_uint64),
+                ("zero_copy_calls", C.c_uint64)]
 
 
 class StridedB200Error(RuntimeError):

@@ -153,6 +153,7 @@ struct sb_ctx {
     // occupancy cache: kernel function -> (smem -> blocks/SM)
     std::map<std::pair<const void *, size_t>, int> occ;
     // host staging pool (sb_mapreduce_host)
+    bool host_zero_copy = true; // SB_HOST_ZERO_COPY=0 turns the zero-copy mode of synchronous calls off
     void *stage = nullptr;
     size_t stage_bytes = 0;
     std::unordered_map<std::string, CachedPlan> plans;
@@ -234,6 +235,7 @@ int sb_ctx_create(int device, void *stream, sb_ctx **out)
     }
     c->dev.sm_count = prop.multiProcessorCount;
     c->dev.ctas_per_sm = 4;
+    if (const char *e = std::getenv("SB_HOST_ZERO_COPY")) c->host_zero_copy = std::atoi(e) != 0;
     if (stream) {
         c->stream = (cudaStream_t)stream;
     } else {
@@ -390,13 +392,14 @@ static cudaError_t launch_jit(const void *fn, unsigned grid, size_t smem, cudaSt
     return cudaLaunchKernelExC(&cfg, fn, args);
 }
 
-// `peer` != nullptr: collective call (sb_mapreduce_allreduce).  If the plan is a reduction with a single output tile whose
-// accumulator type equals the output type, the exchange across GPUs is fused into the reduction kernel (*fused = true);
-// otherwise NOTHING is launched (*fused = false) and the caller runs the two-kernel path.
-static int run_desc(sb_ctx *ctx, const sb_desc &desc, const PeerLink *peer = nullptr, bool *fused = nullptr)
+typedef std::unordered_map<std::string, CachedPlan>::iterator PlanIt;
+
+// plan cache: everything but the base pointers (the reference re-plans on every call; config 3 is ~2 us
+// of device work, so planning must not be on the critical path).  `hostlink`: the operands live in pinned HOST memory and
+// are read / written by the kernel itself (zero-copy mode of sb_mapreduce_host): the planner then fuses aliased views
+// from two views on, because every byte that crosses the host link twice costs twice.
+static int lookup_plan(sb_ctx *ctx, const sb_desc &desc, bool hostlink, PlanIt &hit)
 {
-    // plan cache: everything but the base pointers (the reference re-plans on every call; config 3 is ~2 us
-    // of device work, so planning must not be on the critical path)
     sb_desc keyd;
     std::memset(&keyd, 0, sizeof keyd); // field-wise copy below: struct padding must not leak into the key
     keyd.ndim = desc.ndim;
@@ -436,12 +439,15 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc, const PeerLink *peer = nul
     for (int k = keyd.nops; k < SB_MAX_OPS; ++k) keyd.dtype[k] = keyd.conj[k] = 0;
     for (int i = (keyd.ntok > 0 ? keyd.ntok : 0); i < SB_MAX_TOKENS; ++i) keyd.prog[i] = sb_tok{0, 0, 0.0, 0.0};
     std::string key((const char *)&keyd, sizeof keyd);
+    key.push_back(hostlink ? 'H' : 'D');
     int rc;
-    auto hit = ctx->plans.find(key);
+    hit = ctx->plans.find(key);
     if (hit == ctx->plans.end()) {
         Plan fresh;
         std::string err;
-        rc = build_plan(desc, ctx->dev, fresh, err);
+        DeviceInfo dinfo = ctx->dev;
+        dinfo.host_link = hostlink;
+        rc = build_plan(desc, dinfo, fresh, err);
         if (rc != SB_OK) return set_err(ctx, rc, err);
         ctx->stats.plans_built++;
         if (ctx->plans.size() > 4096) clear_plans(ctx);
@@ -481,6 +487,17 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc, const PeerLink *peer = nul
     } else {
         ctx->stats.plans_cached++;
     }
+    return SB_OK;
+}
+
+// `peer` != nullptr: collective call (sb_mapreduce_allreduce).  If the plan is a reduction with a single output tile whose
+// accumulator type equals the output type, the exchange across GPUs is fused into the reduction kernel (*fused = true);
+// otherwise NOTHING is launched (*fused = false) and the caller runs the two-kernel path.
+static int run_desc(sb_ctx *ctx, const sb_desc &desc, const PeerLink *peer = nullptr, bool *fused = nullptr, bool hostlink = false)
+{
+    PlanIt hit;
+    int rc = lookup_plan(ctx, desc, hostlink, hit);
+    if (rc != SB_OK) return rc;
     Plan plan = hit->second.plan; // copy: bases are bound per call
     plan.map.tile_order = (const int32_t *)hit->second.dev_order;
     plan.map.tile_desc = (const TileDesc *)hit->second.dev_desc;
@@ -596,7 +613,7 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc, const PeerLink *peer = nul
         const size_t counters_bytes = 64 * 1024;
         if (plan.red.nsplit > 1 && (size_t)plan.red.nouttiles * 4 > counters_bytes) return set_err(ctx, SB_E_UNSUPPORTED, "too many output tiles for a split reduction");
         size_t scratch_need = plan.red.nsplit > 1 ? counters_bytes + (size_t)plan.scratch_bytes : 0;
-        if (plan.stream_ok) scratch_need = std::max(scratch_need, counters_bytes + (size_t)plan.stream_grid * 16);
+        if (plan.stream_ok) scratch_need = std::max(scratch_need, counters_bytes + (size_t)plan.stream_grid * (size_t)plan.stream.nout * 16);
         if (scratch_need > ctx->scratch_bytes) {
             if (ctx->scratch) {
                 cudaStreamSynchronize(ctx->stream);
@@ -1046,6 +1063,75 @@ extern "C" int sb_mapreduce_host(sb_ctx *ctx, const sb_desc *desc)
         total += ((s.hi - s.lo) + 255) & ~(size_t)255;
     }
     cudaSetDevice(ctx->device);
+    // does the output need its previous contents on the device?  yes if it is read (op / initop) or if
+    // the written elements do not cover its byte range densely (strided destination)
+    bool out_dense = !any_zero;
+    if (out_dense) {
+        int64_t cnt = 1;
+        for (int i = 0; i < d.ndim; ++i)
+            if (d.strides[0][i] != 0) cnt *= d.dims[i];
+        out_dense = (uintptr_t)(cnt * dtype_size(d.dtype[0])) == (ohi[0] - olo[0]);
+    }
+    // ---- zero-copy mode ------------------------------------------------------------------------------------------
+    // A synchronous call on PINNED host operands: the kernel reads its inputs straight from host memory and writes the
+    // result straight into host memory (unified addressing), so the two directions of the host link overlap inside ONE
+    // launch instead of running H2D copy -> kernel -> D2H copy back to back.  Measured on config 2 (profiles/
+    // r02_a_exp.txt): 3.56 ms against 4.62 ms staged.  Taken only when every input byte crosses the link once: maps
+    // (no read of the output), inputs that do not alias each other -- or alias as permuted views of one parent, which
+    // the orbit kernel fetches once -- and no broadcast (zero-stride) re-reads.  Stream-ordered (sync == 0) callers keep
+    // the staged path: pipelining consecutive calls on the copy engines gets closer to the link rate than SM-issued
+    // stores do (94 vs 72 GB/s on config 2).
+    if (ctx->sync && ctx->host_zero_copy && d.op == SB_OP_NONE && out_dense && d.nops >= 2 && !merged.empty()) {
+        bool ok = true, alias = false;
+        for (int k = 1; k < d.nops && ok; ++k)
+            for (int i = 0; i < d.ndim; ++i)
+                if (d.strides[k][i] == 0 && d.dims[i] > 1) ok = false;
+        for (const Seg &s0 : merged) {
+            int nin_here = 0;
+            for (int k = 1; k < d.nops; ++k)
+                if (olo[k] >= s0.lo && olo[k] < s0.hi) ++nin_here;
+            if (nin_here > 1) alias = true;
+            if (s0.has_in && s0.has_out) ok = false; // in-place: keep the staged path
+        }
+        std::vector<uintptr_t> devlo(merged.size(), 0);
+        for (size_t q = 0; q < merged.size() && ok; ++q) {
+            cudaPointerAttributes a0, a1;
+            if (cudaPointerGetAttributes(&a0, (const void *)merged[q].lo) != cudaSuccess ||
+                cudaPointerGetAttributes(&a1, (const void *)(merged[q].hi - 1)) != cudaSuccess) {
+                cudaGetLastError();
+                ok = false;
+                break;
+            }
+            if (a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost || !a0.devicePointer || !a1.devicePointer ||
+                (uintptr_t)a1.devicePointer - (uintptr_t)a0.devicePointer != merged[q].hi - 1 - merged[q].lo)
+                ok = false;
+            else
+                devlo[q] = (uintptr_t)a0.devicePointer;
+        }
+        if (ok) {
+            sb_desc dz = d;
+            for (int k = 0; k < d.nops; ++k)
+                for (size_t q = 0; q < merged.size(); ++q)
+                    if (olo[k] >= merged[q].lo && olo[k] < merged[q].hi) dz.base[k] = (void *)(devlo[q] + ((uintptr_t)d.base[k] - merged[q].lo));
+            if (alias) { // only worth it if the aliased views are fetched once (orbit plan)
+                PlanIt hit;
+                const int rc0 = lookup_plan(ctx, dz, true, hit);
+                if (rc0 != SB_OK || !hit->second.plan.orbit_ok) ok = false;
+            }
+            if (ok) {
+                const int rc1 = run_desc(ctx, dz, nullptr, nullptr, true);
+                if (rc1 != SB_OK) return rc1;
+                for (const Seg &s0 : merged) {
+                    if (s0.has_in) ctx->stats.h2d_bytes += s0.hi - s0.lo;
+                    if (s0.has_out) ctx->stats.d2h_bytes += s0.hi - s0.lo;
+                }
+                ctx->stats.zero_copy_calls++;
+                cudaError_t e = cudaStreamSynchronize(ctx->stream);
+                if (e != cudaSuccess) return cuda_fail(ctx, e, "sb_mapreduce_host (zero-copy)");
+                return SB_OK;
+            }
+        }
+    }
     if (total > ctx->stage_bytes) {
         if (ctx->stage) {
             cudaStreamSynchronize(ctx->stream);
@@ -1057,15 +1143,7 @@ extern "C" int sb_mapreduce_host(sb_ctx *ctx, const sb_desc *desc)
         if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(stage)");
         ctx->stage_bytes = total;
     }
-    // 2. does the output need its previous contents on the device?  yes if it is read (op / initop) or if
-    //    the written elements do not cover its byte range densely (strided destination)
-    bool out_dense = !any_zero;
-    if (out_dense) {
-        int64_t cnt = 1;
-        for (int i = 0; i < d.ndim; ++i)
-            if (d.strides[0][i] != 0) cnt *= d.dims[i];
-        out_dense = (uintptr_t)(cnt * dtype_size(d.dtype[0])) == (ohi[0] - olo[0]);
-    }
+    // 2. stage the inputs (and the output's previous contents when they are read, see out_dense above)
     const bool out_read = d.op != SB_OP_NONE || !out_dense;
     for (const Seg &s : merged) {
         if (!(s.has_in || (s.has_out && out_read))) continue;

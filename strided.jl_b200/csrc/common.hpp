@@ -360,14 +360,24 @@ struct ReduceParams {
 // mbarrier complete_tx) from the first cycle on, eight consumer warps fold the landed chunks out of shared memory with
 // 128-bit loads; CTA partials meet in a fixed order in the last-arriving CTA (one acq_rel atomic per CTA, no fences).
 // GPU analog of the per-task partial slots + serial fold of the reference (src/mapreduce.jl:153-170).
+// The same kernel serves a FEW outputs whose reduction ranges are each one dense run (`mapreduce(f, op, A; dims=(1,2))`
+// of a 3-D array; config 5 with several dense slices per GPU): the outputs are streamed one after the other through the
+// same ring, every CTA leaves one partial per output.
+constexpr int STREAM_MAXKD = 4;   // kept dims (after canonical fusing)
+constexpr int STREAM_MAXOUT = 64; // outputs
 struct StreamParams {
-    int64_t nelem;       // elements per input (every input is dense, stride 1, the accumulator's type)
-    int64_t vec_bytes;   // bytes per input covered by whole 16-byte vectors (the <16-byte rest is folded by one thread)
-    int64_t nchunks;     // ceil(vec_bytes / chunk_bytes)
+    int64_t nelem;       // elements per input PER OUTPUT (every run is dense, stride 1, the accumulator's type)
+    int64_t vec_bytes;   // bytes of a run covered by whole 16-byte vectors (the <16-byte rest is folded by one thread)
+    int64_t nchunks;     // chunks per output: ceil(vec_bytes / chunk_bytes)
     int32_t nin;
     int32_t chunk_bytes; // per input per stage (multiple of 16)
     int32_t nstage;
     int32_t stage_bytes; // nin * chunk_bytes
+    int32_t nout;        // outputs = product of kdims (1: complete reduction)
+    int32_t nkd;         // kept dims
+    int64_t kdims[STREAM_MAXKD];
+    int64_t kin_bytes[MAXIN][STREAM_MAXKD]; // byte stride of input k along kept dim d (multiple of 16)
+    int64_t kout_bytes[STREAM_MAXKD];       // byte stride of the output along kept dim d
 };
 
 // ---- in-tile linear index of element (t, j) -----------------------------------------------------------------

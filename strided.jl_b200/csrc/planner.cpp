@@ -1135,13 +1135,14 @@ bool orbit_thread_map(const OrbitGeom &G, int (*ebit)[16], uint32_t *col)
 
 // Fills plan.orbit* when every input is a dim-permuted view of one parent and the output's fastest dim is moved
 // by at least one of the permutations (the transposing case).  `prog` is the matched recipe of the map plan.
-bool plan_orbit(const Canon &c, const Program &prog, Plan &plan)
+bool plan_orbit(const Canon &c, const Program &prog, Plan &plan, const DeviceInfo &dev)
 {
     if (std::getenv("SB_NO_ORBIT")) return false;
     // Two aliased views (A and A'): the TMA ring kernel (two loads through L2, alias-aware tile order) measures
     // 43.7 us on config 2 against 44.8-46 us here (profiles/r01_v9_orbit_tma_vs_lsu_breakdown.txt) -- both are bound by
     // the ~20 B/clk/SM the TMA unit moves -- so the fused path is taken from three views on, where it wins 3x.
-    if (c.nops - 1 == 2 && !std::getenv("SB_ORBIT_NIN2")) return false;
+    // (across the host link -- zero-copy mode of sb_mapreduce_host -- a second fetch of the parent costs a full transfer)
+    if (c.nops - 1 == 2 && !dev.host_link && !std::getenv("SB_ORBIT_NIN2")) return false;
     OrbitGeom G;
     if (!orbit_family(c, G) || !orbit_tile_bits(c, G)) return false;
     const int n = G.n, nin = G.nin, esz = G.esz, ebits = G.ebits;
@@ -1566,7 +1567,7 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
     }
     plan.elements = 1;
     for (int i = 0; i < n; ++i) plan.elements *= c.dims[i];
-    if (uniform && plan_orbit(c, P.prog, plan)) plan.note = "alias-fused orbits";
+    if (uniform && plan_orbit(c, P.prog, plan, dev)) plan.note = "alias-fused orbits";
     return SB_OK;
 }
 
@@ -1579,24 +1580,40 @@ bool stream_instantiated(int ct, int recipe, int nin_t)
     return false;
 }
 
-// Streamed variant (common.hpp "StreamParams"): complete reduction, every input one dense run of the accumulator's type.
+// Streamed variant (common.hpp "StreamParams"): every output's reduction range is ONE dense run of the accumulator's
+// type in every input -- complete reductions (no kept dim) and reductions over the leading dims of a dense array
+// (`mapreduce(f, op, A; dims=(1,2))`, config 5 with several dense slices per GPU) with at most STREAM_MAXOUT outputs.
 void plan_stream(const Canon &c, const DeviceInfo &dev, bool uniform, Plan &plan)
 {
     if (std::getenv("SB_NO_STREAM")) return;
     const int nin = c.nops - 1, esz = dtype_size(c.ct);
-    if (c.nkept != 0 || c.ndim != 1 || !uniform || nin < 1 || nin > 3) return;
+    if (c.ndim != c.nkept + 1 || c.nkept > STREAM_MAXKD || !uniform || nin < 1 || nin > 3) return;
+    const int r = c.nkept; // the (fused) reduced dim
     for (int k = 1; k <= nin; ++k)
-        if (c.strides[k][0] != 1) return;
+        if (c.strides[k][r] != 1) return;
     if (!stream_instantiated(plan.key.ct, plan.key.recipe, plan.key.nin)) return;
     StreamParams &S = plan.stream;
     std::memset(&S, 0, sizeof S);
-    S.nelem = c.dims[0];
+    int64_t nout = 1;
+    S.nkd = c.nkept;
+    for (int d = 0; d < c.nkept; ++d) {
+        S.kdims[d] = c.dims[d];
+        nout *= c.dims[d];
+        if (nout > STREAM_MAXOUT) return;
+        S.kout_bytes[d] = c.strides[0][d] * dtype_size(c.dtype[0]);
+        for (int k = 1; k <= nin; ++k) {
+            S.kin_bytes[k - 1][d] = c.strides[k][d] * esz;
+            if (S.kin_bytes[k - 1][d] % 16 != 0) return; // every run starts on a 16-byte boundary (cp.async.bulk)
+        }
+    }
+    S.nout = (int32_t)nout;
+    S.nelem = c.dims[r];
     if (S.nelem > ((int64_t)1 << 56) / esz) return;
     S.vec_bytes = (S.nelem * esz) & ~(int64_t)15;
     if (S.vec_bytes < 64 * 1024) return; // (one or two CTAs of the tiled kernel do as well below that)
     S.nin = nin;
     // chunk per input: 32 KB / nin at most (four stages of 32 KB keep ~19 MB in flight over 148 SMs), smaller when the
-    // problem would otherwise leave SMs without a chunk: aim for two chunks per CTA
+    // problem would otherwise leave SMs without a chunk: aim for two chunks per CTA and output
     int64_t chunk = 32 * 1024 / (nin == 3 ? 4 : nin);
     const int64_t want = S.vec_bytes / (2 * (int64_t)dev.sm_count);
     while (chunk > 4096 && chunk > want) chunk >>= 1;
@@ -1893,7 +1910,7 @@ std::string describe_plan(const Plan &p)
            << ",\"nout_tile\":" << P.nout_tile << ",\"nred_tile\":" << P.nred_tile
            << ",\"warp_per_output\":" << P.warp_per_output << ",\"scratch_bytes\":" << p.scratch_bytes;
         if (p.stream_ok)
-            os << ",\"stream\":{\"grid\":" << p.stream_grid << ",\"chunk_bytes\":" << p.stream.chunk_bytes << ",\"nstage\":" << p.stream.nstage
+            os << ",\"stream\":{\"grid\":" << p.stream_grid << ",\"nout\":" << p.stream.nout << ",\"chunk_bytes\":" << p.stream.chunk_bytes << ",\"nstage\":" << p.stream.nstage
                << ",\"nchunks\":" << p.stream.nchunks << ",\"smem_bytes\":" << p.stream_smem_bytes << "}";
     }
     os << "}";

@@ -17,6 +17,7 @@ enum PlanKind : int { PLAN_NOOP = 0, PLAN_MAP = 1, PLAN_REDUCE = 2 };
 struct DeviceInfo {
     int sm_count = 148;        // B200
     int ctas_per_sm = 4;       // resident CTAs of THREADS threads assumed for grid sizing
+    bool host_link = false;    // operands are pinned HOST memory accessed by the kernel (zero-copy): fuse aliased views from 2 views on
 };
 
 struct KernelKey {

@@ -70,17 +70,44 @@ SB_HD void stream_chunk(const ReduceParams &P, const StreamParams &S, const unsi
     }
 }
 
-// the < 16-byte rest of the inputs (elements [vec_bytes / sizeof(AT), nelem)), read straight from the operands
-template <class AT, int RC, int NIN> SB_HD AT stream_rest(const ReduceParams &P, const StreamParams &S, AT acc)
+// byte offset of output number o (kept dim 0 fastest): in input k's parent (k >= 0) or in the output (k < 0)
+SB_HD int64_t stream_out_offset(const StreamParams &S, int o, int k)
+{
+    int64_t off = 0;
+#pragma unroll
+    for (int d = 0; d < STREAM_MAXKD; ++d) {
+        if (d < S.nkd) {
+            const int64_t c = (int64_t)o % S.kdims[d];
+            o = (int)((int64_t)o / S.kdims[d]);
+            off += c * (k < 0 ? S.kout_bytes[d] : S.kin_bytes[k][d]);
+        }
+    }
+    return off;
+}
+
+// the < 16-byte rest of output o's runs (elements [vec_bytes / sizeof(AT), nelem)), read straight from the operands
+template <class AT, int RC, int NIN> SB_HD AT stream_rest(const ReduceParams &P, const StreamParams &S, int o, AT acc)
 {
     ElemFn<AT, RC> fn;
     for (int64_t e = S.vec_bytes / (int64_t)sizeof(AT); e < S.nelem; ++e) {
         AT a[NIN];
 #pragma unroll
-        for (int k = 0; k < NIN; ++k) a[k] = reinterpret_cast<const AT *>(P.base[(k < S.nin ? k : 0) + 1])[e];
+        for (int k = 0; k < NIN; ++k) {
+            const int kk = k < S.nin ? k : 0;
+            a[k] = reinterpret_cast<const AT *>(P.base[kk + 1] + stream_out_offset(S, o, kk))[e];
+        }
         acc = red_apply<AT>(P.op, acc, fn.template eval<NIN>(P.prog, a));
     }
     return acc;
+}
+
+// out[o] = op(initop(out[o]), total)   (reference src/mapreduce.jl:314 with the initop of :351-382)
+template <class AT> SB_HD void stream_store(const ReduceParams &P, const StreamParams &S, int o, AT total)
+{
+    unsigned char *dst = P.base[0] + stream_out_offset(S, o, -1);
+    AT x = load_elem<AT, true>(dst, P.dtype[0], P.conj[0]);
+    x = init_apply<AT>(P.initop, P.init_re, P.init_im, x);
+    store_elem<AT, true>(dst, P.dtype[0], P.conj[0], red_apply<AT>(P.op, x, total));
 }
 
 // the four accumulators of a thread, in slot order

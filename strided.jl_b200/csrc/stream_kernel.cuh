@@ -31,8 +31,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) reduce_stream_kernel(const 
     extern __shared__ unsigned char sb_stream_smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STREAM_MAXSTAGE];
     __shared__ __align__(8) uint64_t empty_bar[STREAM_MAXSTAGE];
-    __shared__ __align__(16) unsigned char fold_raw[(THREADS / 32) * sizeof(AT)];
-    __shared__ unsigned int is_last;
+    __shared__ __align__(16) unsigned char fold_raw[2 * (THREADS / 32) * sizeof(AT)];
+    __shared__ unsigned int is_last, s_epoch;
     AT *fold = reinterpret_cast<AT *>(fold_raw);
     unsigned char *ring = sb_stream_smem_raw + ((0u - smem_u32(sb_stream_smem_raw)) & 127u);
     const uint32_t ring_u32 = smem_u32(ring);
@@ -50,37 +50,43 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) reduce_stream_kernel(const 
     pdl_wait(); // operands, output, partials and the arrival counter may all be in use by the previous kernel
     const int64_t nchunks = S.nchunks;
     const uint32_t grid = gridDim.x;
+    const int nout = S.nout;
     if (warp == THREADS / 32) {
         // ---------------- producer ----------------
         if (lane == 0) {
             int stage = 0;
             uint32_t parity = 1; // a fresh barrier passes a wait on parity 1: every stage starts out empty
-            for (int64_t c = blockIdx.x; c < nchunks; c += grid) {
-                mbar_wait(smem_u32(&empty_bar[stage]), parity);
-                const int64_t off = c * (int64_t)S.chunk_bytes;
-                const int64_t left = S.vec_bytes - off;
-                const uint32_t nb = (uint32_t)(left < (int64_t)S.chunk_bytes ? left : (int64_t)S.chunk_bytes);
-                const uint32_t fb = smem_u32(&full_bar[stage]);
-                mbar_expect_tx(fb, nb * (uint32_t)S.nin);
-                const uint32_t dst = ring_u32 + (uint32_t)(stage * S.stage_bytes);
+            for (int o = 0; o < nout; ++o) {
+                const unsigned char *src[NIN];
 #pragma unroll
-                for (int k = 0; k < NIN; ++k)
-                    if (k < S.nin) bulk_load_1d(dst + (uint32_t)(k * S.chunk_bytes), P.base[k + 1] + off, nb, fb);
-                if (++stage == NS) {
-                    stage = 0;
-                    parity ^= 1u;
+                for (int k = 0; k < NIN; ++k) src[k] = P.base[(k < S.nin ? k : 0) + 1] + stream_out_offset(S, o, k < S.nin ? k : 0);
+                for (int64_t c = blockIdx.x; c < nchunks; c += grid) {
+                    mbar_wait(smem_u32(&empty_bar[stage]), parity);
+                    const int64_t off = c * (int64_t)S.chunk_bytes;
+                    const int64_t left = S.vec_bytes - off;
+                    const uint32_t nb = (uint32_t)(left < (int64_t)S.chunk_bytes ? left : (int64_t)S.chunk_bytes);
+                    const uint32_t fb = smem_u32(&full_bar[stage]);
+                    mbar_expect_tx(fb, nb * (uint32_t)S.nin);
+                    const uint32_t dst = ring_u32 + (uint32_t)(stage * S.stage_bytes);
+#pragma unroll
+                    for (int k = 0; k < NIN; ++k)
+                        if (k < S.nin) bulk_load_1d(dst + (uint32_t)(k * S.chunk_bytes), src[k] + off, nb, fb);
+                    if (++stage == NS) {
+                        stage = 0;
+                        parity ^= 1u;
+                    }
                 }
             }
         }
         return;
     }
     // ---------------- consumers ----------------
-    AT acc[STREAM_ACC];
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int o = 0; o < nout; ++o) {
+        AT acc[STREAM_ACC];
 #pragma unroll
-    for (int q = 0; q < STREAM_ACC; ++q) acc[q] = red_neutral<AT>(P.op);
-    {
-        int stage = 0;
-        uint32_t parity = 0;
+        for (int q = 0; q < STREAM_ACC; ++q) acc[q] = red_neutral<AT>(P.op);
         for (int64_t c = blockIdx.x; c < nchunks; c += grid) {
             const int64_t left = S.vec_bytes - c * (int64_t)S.chunk_bytes;
             const int nv = (int)((left < (int64_t)S.chunk_bytes ? left : (int64_t)S.chunk_bytes) >> 4);
@@ -93,53 +99,49 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) reduce_stream_kernel(const 
                 parity ^= 1u;
             }
         }
-    }
-    AT p = stream_thread_total<AT>(P, acc);
-    if (blockIdx.x == 0 && tid == 0) p = stream_rest<AT, RC, NIN>(P, S, p);
+        AT p = stream_thread_total<AT>(P, acc);
+        if (blockIdx.x == 0 && tid == 0) p = stream_rest<AT, RC, NIN>(P, S, o, p);
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) p = red_apply<AT>(P.op, p, shfl_xor_any(p, m));
-    if (lane == 0) fold[warp] = p;
-    asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); // consumers only: the producer warp has retired
-    AT q = red_neutral<AT>(P.op);
-    if (tid == 0) {
-        q = fold[0];
-#pragma unroll
-        for (int w = 1; w < THREADS / 32; ++w) q = red_apply<AT>(P.op, q, fold[w]);
-    }
-    if (grid > 1) {
+        for (int m = 16; m >= 1; m >>= 1) p = red_apply<AT>(P.op, p, shfl_xor_any(p, m));
+        AT *fb = fold + (o & 1) * (THREADS / 32); // two buffers: thread 0 reads output o's while the others fill o + 1's
+        if (lane == 0) fb[warp] = p;
+        asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); // consumers only: the producer warp has retired
         if (tid == 0) {
-            reinterpret_cast<AT *>(P.scratch)[blockIdx.x] = q;
-            unsigned int old;
-            asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(P.counters) : "memory");
-            is_last = (old == grid - 1u) ? 1u : 0u;
+            AT q = fb[0];
+#pragma unroll
+            for (int w = 1; w < THREADS / 32; ++w) q = red_apply<AT>(P.op, q, fb[w]);
+            reinterpret_cast<AT *>(P.scratch)[(size_t)o * grid + blockIdx.x] = q; // this CTA's partial of output o
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
-        if (!is_last) return;
-        // the last-arriving CTA: fold the CTA partials in CTA order (thread t takes t, t + 256, ...)
-        const AT *sc = reinterpret_cast<const AT *>(P.scratch);
+    }
+    if (tid == 0) {
+        unsigned int old = grid - 1u;
+        if (grid > 1) asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(P.counters) : "memory");
+        is_last = (old == grid - 1u) ? 1u : 0u;
+        if (is_last) {
+            if (grid > 1) *P.counters = 0u; // re-arm for the next launch (stream-ordered: nobody else touches it before)
+            uint32_t epoch = 0u;
+            if (P.peer.world > 1) { // collective call: the call number lives on the device (graph-replay safe)
+                epoch = __ldcg(P.peer.epoch_ptr) + 1u;
+                __stcg(P.peer.epoch_ptr, epoch);
+            }
+            s_epoch = epoch;
+        }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+    if (!is_last) return;
+    // the last-arriving CTA: warp w folds the CTA partials of outputs w, w + 8, ... in CTA order (lane l takes l, l + 32, ...)
+    const AT *sc = reinterpret_cast<const AT *>(P.scratch);
+    for (int o = warp; o < nout; o += THREADS / 32) {
         AT r = red_neutral<AT>(P.op);
-        for (uint32_t i = (uint32_t)tid; i < grid; i += THREADS) r = red_apply<AT>(P.op, r, load_partial(sc + i));
+        for (uint32_t i = (uint32_t)lane; i < grid; i += 32) r = red_apply<AT>(P.op, r, load_partial(sc + (size_t)o * grid + i));
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) r = red_apply<AT>(P.op, r, shfl_xor_any(r, m));
-        asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); // fold[] has been read by thread 0 above
-        if (lane == 0) fold[warp] = r;
-        asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
-        if (tid == 0) {
-            q = fold[0];
-#pragma unroll
-            for (int w = 1; w < THREADS / 32; ++w) q = red_apply<AT>(P.op, q, fold[w]);
-            *P.counters = 0u; // re-arm for the next launch (stream-ordered: nobody else touches it before)
-        }
-    }
-    if (tid == 0) {
-        if constexpr (sizeof(AT) <= 8) {
-            if (P.peer.world > 1) { // collective call: one value per rank crosses NVLink, folded in rank order
-                const uint32_t epoch = __ldcg(P.peer.epoch_ptr) + 1u;
-                __stcg(P.peer.epoch_ptr, epoch);
-                q = peer_ll_allreduce<AT>(P, 0, q, epoch);
+        if (lane == 0) {
+            if constexpr (sizeof(AT) <= 8) {
+                if (P.peer.world > 1) r = peer_ll_exchange<AT>(P, o, r, s_epoch); // one value per rank crosses NVLink, folded in rank order
             }
+            stream_store<AT>(P, S, o, r);
         }
-        red_finalize_store<AT, true>(P, 0, q);
     }
 }
 

@@ -155,8 +155,21 @@ def stream_reduction_cases(n=70001):
         out.append(Case(f"stream_3in_{nm}", [np.zeros(1, dt), x, y, z], [O, X, Y, Z], [A(0), A(1), F("mul"), A(2), F("div")], op=1, rtol=tol * 50))
         out.append(Case(f"stream_sum_off1_{nm}", [np.zeros(1, dt), x], [O, ViewSpec(1, 1, (n,), (1,))], P_COPY, op=1, rtol=tol))
         out.append(Case(f"stream_sum_even_{nm}", [np.zeros(1, dt), x], [ViewSpec(0, 0, (n - 1,), (0,)), ViewSpec(1, 0, (n - 1,), (1,))], P_COPY, op=1, rtol=tol))
+        # a FEW outputs, each reducing one dense run: mapreduce(f, op, A; dims=(1,2)) of a 3-D array (config 5 with several
+        # dense slices per GPU), also through a permuted output, a stepped kept dim, and two kept dims
+        m1, m2, g = (n // 3) // 2 * 2, 3, 5
+        a3 = (rand(rng, m1 * m2 * g * 2, dt) - 0.5).astype(dt)
+        A3 = ViewSpec(1, 0, (m1, m2, g), (1, m1, m1 * m2))
+        out.append(Case(f"stream_dims12_{nm}", [np.full(g, 2, dt), a3], [ViewSpec(0, 0, (m1, m2, g), (0, 0, 1)), A3], P_COPY, op=1, rtol=tol))
+        out.append(Case(f"stream_dims12_init0_rev_{nm}", [np.full(g, 2, dt), a3], [ViewSpec(0, g - 1, (m1, m2, g), (0, 0, -1)), A3], P_COPY,
+                        op=1, initop=1, rtol=tol))
+        out.append(Case(f"stream_dims12_step2_{nm}", [np.zeros(g, dt), a3], [ViewSpec(0, 0, (m1, m2, g), (0, 0, 1)),
+                                                                             ViewSpec(1, 0, (m1, m2, g), (1, m1, 2 * m1 * m2))], P_COPY, op=1, rtol=tol))
+        A4 = ViewSpec(1, 0, (m1 * m2 // 2, 2, g), (1, m1 * m2 // 2, m1 * m2))  # kept dims 2 x g, runs of m1*m2/2
+        out.append(Case(f"stream_2kept_{nm}", [np.zeros(2 * g, dt), a3], [ViewSpec(0, 0, (m1 * m2 // 2, 2, g), (0, g, 1)), A4], P_COPY, op=1, rtol=tol))
         if np.dtype(dt).kind == "f":
             out.append(Case(f"stream_abs2_{nm}", [np.zeros(1, dt), x], [O, X], [A(0), F("abs2")], op=1, rtol=tol))
+            out.append(Case(f"stream_dims12_max_{nm}", [np.full(g, -9, dt), a3], [ViewSpec(0, 0, (m1, m2, g), (0, 0, 1)), A3], [A(0), F("abs")], op=4))
             out.append(Case(f"stream_max_{nm}", [np.full(1, -9, dt), x], [O, X], P_COPY, op=4))
             out.append(Case(f"stream_min_{nm}", [np.full(1, 9, dt), x], [O, X], P_COPY, op=3))
             small = (1 + (rand(rng, 4100 * (8 // np.dtype(dt).itemsize) * 2, dt) - 0.5) * 1e-3).astype(dt)

@@ -243,51 +243,47 @@ template <class AT, int RC, int NIN> static void run_stream(const Plan &plan)
     const int grid = (int)plan.stream_grid;
     std::vector<unsigned char> raw((size_t)S.stage_bytes + 64);
     unsigned char *stage = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(raw.data()) + 15) & ~(uintptr_t)15);
-    std::vector<AT> partials((size_t)grid);
+    std::vector<AT> partials((size_t)grid * (size_t)S.nout);
     using Acc = AT[STREAM_ACC];
     for (int b = 0; b < grid; ++b) {
-        std::vector<char> accbuf(sizeof(Acc) * THREADS);
-        Acc *acc = reinterpret_cast<Acc *>(accbuf.data());
-        for (int t = 0; t < THREADS; ++t)
-            for (int q = 0; q < STREAM_ACC; ++q) acc[t][q] = red_neutral<AT>(P.op);
-        for (int64_t c = b; c < S.nchunks; c += grid) {
-            const int64_t off = c * (int64_t)S.chunk_bytes;
-            const int64_t left = S.vec_bytes - off;
-            const int64_t nb = left < S.chunk_bytes ? left : S.chunk_bytes;
-            std::memset(stage, 0xCD, (size_t)S.stage_bytes);
-            for (int k = 0; k < S.nin; ++k) std::memcpy(stage + (size_t)k * S.chunk_bytes, P.base[k + 1] + off, (size_t)nb);
-            for (int t = 0; t < THREADS; ++t) stream_chunk<AT, RC, NIN>(P, S, stage, (int)(nb >> 4), t, acc[t]);
-        }
-        AT wres[THREADS / 32];
-        for (int w = 0; w < THREADS / 32; ++w) {
-            AT p[32];
-            for (int lane = 0; lane < 32; ++lane) {
-                const int t = w * 32 + lane;
-                p[lane] = stream_thread_total<AT>(P, acc[t]);
-                if (b == 0 && t == 0) p[lane] = stream_rest<AT, RC, NIN>(P, S, p[lane]);
+        for (int o = 0; o < S.nout; ++o) {
+            std::vector<char> accbuf(sizeof(Acc) * THREADS);
+            Acc *acc = reinterpret_cast<Acc *>(accbuf.data());
+            for (int t = 0; t < THREADS; ++t)
+                for (int q = 0; q < STREAM_ACC; ++q) acc[t][q] = red_neutral<AT>(P.op);
+            for (int64_t c = b; c < S.nchunks; c += grid) {
+                const int64_t off = c * (int64_t)S.chunk_bytes;
+                const int64_t left = S.vec_bytes - off;
+                const int64_t nb = left < S.chunk_bytes ? left : S.chunk_bytes;
+                std::memset(stage, 0xCD, (size_t)S.stage_bytes);
+                for (int k = 0; k < S.nin; ++k)
+                    std::memcpy(stage + (size_t)k * S.chunk_bytes, P.base[k + 1] + stream_out_offset(S, o, k) + off, (size_t)nb);
+                for (int t = 0; t < THREADS; ++t) stream_chunk<AT, RC, NIN>(P, S, stage, (int)(nb >> 4), t, acc[t]);
             }
-            wres[w] = butterfly<AT>(P, p);
-        }
-        AT q = wres[0];
-        for (int w = 1; w < THREADS / 32; ++w) q = red_apply<AT>(P.op, q, wres[w]);
-        partials[(size_t)b] = q;
-    }
-    AT total = partials[0];
-    if (grid > 1) {
-        AT wres[THREADS / 32];
-        for (int w = 0; w < THREADS / 32; ++w) {
-            AT p[32];
-            for (int lane = 0; lane < 32; ++lane) {
-                AT r = red_neutral<AT>(P.op);
-                for (int i = w * 32 + lane; i < grid; i += THREADS) r = red_apply<AT>(P.op, r, partials[(size_t)i]);
-                p[lane] = r;
+            AT wres[THREADS / 32];
+            for (int w = 0; w < THREADS / 32; ++w) {
+                AT p[32];
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int t = w * 32 + lane;
+                    p[lane] = stream_thread_total<AT>(P, acc[t]);
+                    if (b == 0 && t == 0) p[lane] = stream_rest<AT, RC, NIN>(P, S, o, p[lane]);
+                }
+                wres[w] = butterfly<AT>(P, p);
             }
-            wres[w] = butterfly<AT>(P, p);
+            AT q = wres[0];
+            for (int w = 1; w < THREADS / 32; ++w) q = red_apply<AT>(P.op, q, wres[w]);
+            partials[(size_t)o * grid + b] = q;
         }
-        total = wres[0];
-        for (int w = 1; w < THREADS / 32; ++w) total = red_apply<AT>(P.op, total, wres[w]);
     }
-    red_finalize_store<AT, true>(P, 0, total);
+    for (int o = 0; o < S.nout; ++o) { // the last-arriving CTA: one warp per output, lane l folds CTAs l, l + 32, ...
+        AT p[32];
+        for (int lane = 0; lane < 32; ++lane) {
+            AT r = red_neutral<AT>(P.op);
+            for (int i = lane; i < grid; i += 32) r = red_apply<AT>(P.op, r, partials[(size_t)o * grid + i]);
+            p[lane] = r;
+        }
+        stream_store<AT>(P, S, o, butterfly<AT>(P, p));
+    }
 }
 template <class AT> static bool stream_dispatch(const Plan &plan)
 {
