@@ -135,6 +135,9 @@ int sb_ctx_set_stream(sb_ctx *ctx, void *stream);
 /* sync != 0 (default): sb_mapreduce returns after the result is complete, like the reference, which
  * joins its tasks before returning (mapreduce.jl:223).  sync == 0: stream-ordered (benchmarks). */
 int sb_ctx_set_sync(sb_ctx *ctx, int sync);
+/* The SB_* environment knobs are read when a ctx is created, not on the launch path.  A host program that changes them
+ * afterwards (tests, tuning tools) calls this: re-reads them and drops the ctx's cached plans. */
+int sb_ctx_reload_env(sb_ctx *ctx);
 int sb_sync(sb_ctx *ctx);
 const char *sb_last_error(sb_ctx *ctx); /* ctx may be NULL: last error of the calling thread        */
 int sb_abi_version(void);
@@ -190,6 +193,10 @@ int sb_peer_detach(sb_ctx *ctx);
 int sb_mapreduce_allreduce(sb_ctx *ctx, const sb_desc *desc);
 
 /* ---- introspection (no GPU needed) --------------------------------------------------------------
+ * CUDA graphs: a call may be captured (cudaStreamBeginCapture on the ctx's stream, sync == 0) once its plan exists, i.e.
+ * after the same call has run once outside the capture; a first call inside a capture returns SB_E_UNSUPPORTED with a
+ * message instead of invalidating the capture (plan tables and scratch are allocated on the first call).
+ *
  * Writes a one-line JSON description of the plan the host planner picks for `desc` (kernel family,
  * canonical dims, tile extents, staged operands, grid) into buf.  ctx may be NULL. */
 int sb_plan_describe(sb_ctx *ctx, const sb_desc *desc, char *buf, size_t buflen);

@@ -76,7 +76,7 @@ class NoDeviceError(StridedB200Error):
 
 
 EXPORTS = [
-    "sb_abi_version", "sb_ctx_create", "sb_ctx_destroy", "sb_ctx_set_stream", "sb_ctx_set_sync", "sb_sync",
+    "sb_abi_version", "sb_ctx_create", "sb_ctx_destroy", "sb_ctx_set_stream", "sb_ctx_set_sync", "sb_ctx_reload_env", "sb_sync",
     "sb_last_error", "sb_malloc", "sb_free", "sb_memcpy_h2d", "sb_memcpy_d2h", "sb_mapreduce",
     "sb_mapreduce_host", "sb_plan_describe", "sb_get_stats", "sb_reset_stats",
     "sb_peer_export", "sb_peer_attach", "sb_peer_detach", "sb_mapreduce_allreduce",
@@ -84,7 +84,8 @@ EXPORTS = [
 SB_PEER_MAX_OUT, SB_PEER_MAX_WORLD, SB_IPC_HANDLE_BYTES = 1024, 8, 64
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libstrided_b200.so")
+# STRIDED_B200_LIB: explicit path of the shared library (the Julia glue honours the same variable); default: the in-tree build
+LIB_PATH = os.environ.get("STRIDED_B200_LIB") or os.path.join(_PKG_DIR, "libstrided_b200.so")
 _lib = None
 
 
@@ -104,6 +105,7 @@ def load_library():
     lib.sb_ctx_destroy.argtypes = [vp]
     lib.sb_ctx_set_stream.argtypes = [vp, vp]
     lib.sb_ctx_set_sync.argtypes = [vp, i32]
+    lib.sb_ctx_reload_env.argtypes = [vp]
     lib.sb_sync.argtypes = [vp]
     lib.sb_last_error.argtypes = [vp]
     lib.sb_last_error.restype = C.c_char_p

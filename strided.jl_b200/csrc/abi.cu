@@ -53,6 +53,36 @@ const ReduceEntry *find_reduce_kernel(const KernelKey &k)
 
 static thread_local std::string g_tls_err;
 
+namespace sb {
+EnvCache &env_cache()
+{
+    static EnvCache c;
+    return c;
+}
+void env_reload()
+{
+    EnvCache &c = env_cache();
+    c.pdl = std::getenv("SB_NO_PDL") == nullptr;
+    c.fused_peer = std::getenv("SB_NO_FUSED_PEER") == nullptr;
+    const char *e = std::getenv("SB_JIT_MIN_ELEMENTS");
+    c.jit_min_elements = e ? std::atoll(e) : (1ll << 20);
+    c.jit_sync = std::getenv("SB_JIT_SYNC") != nullptr;
+}
+cudaError_t ensure_dynamic_smem(const void *func, size_t smem)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> have;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    size_t &h = have[std::make_pair(dev, func)];
+    if (smem <= h) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) h = smem;
+    return e;
+}
+} // namespace sb
+
 // cuTensorMapEncodeTiled is fetched through the runtime (no link-time dependency on libcuda, so the library
 // also loads on machines without a driver -- where it can only plan, not compute).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -168,6 +198,16 @@ struct sb_ctx {
     void *peer_tmp = nullptr;                    // local partial (SB_PEER_MAX_OUT elements of up to 16 bytes)
 };
 
+static bool stream_is_capturing(sb_ctx *ctx)
+{
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(ctx->stream, &st) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return st != cudaStreamCaptureStatusNone;
+}
+
 static void clear_plans(sb_ctx *ctx)
 {
     cudaStreamSynchronize(ctx->stream);
@@ -236,6 +276,7 @@ int sb_ctx_create(int device, void *stream, sb_ctx **out)
     c->dev.sm_count = prop.multiProcessorCount;
     c->dev.ctas_per_sm = 4;
     if (const char *e = std::getenv("SB_HOST_ZERO_COPY")) c->host_zero_copy = std::atoi(e) != 0;
+    env_reload();
     if (stream) {
         c->stream = (cudaStream_t)stream;
     } else {
@@ -278,6 +319,17 @@ int sb_ctx_set_stream(sb_ctx *ctx, void *stream)
         ctx->own_stream = false;
     }
     ctx->stream = (cudaStream_t)stream;
+    return SB_OK;
+}
+
+int sb_ctx_reload_env(sb_ctx *ctx)
+{
+    if (!ctx) return set_err(nullptr, SB_E_INVALID, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    env_reload();
+    const char *e = std::getenv("SB_HOST_ZERO_COPY");
+    ctx->host_zero_copy = e ? std::atoi(e) != 0 : true;
+    clear_plans(ctx); // plan-time knobs (SB_NO_TMA, SB_ORBIT_*, ...) take effect for the plans built from now on
     return SB_OK;
 }
 
@@ -450,36 +502,36 @@ static int lookup_plan(sb_ctx *ctx, const sb_desc &desc, bool hostlink, PlanIt &
         rc = build_plan(desc, dinfo, fresh, err);
         if (rc != SB_OK) return set_err(ctx, rc, err);
         ctx->stats.plans_built++;
-        if (ctx->plans.size() > 4096) clear_plans(ctx);
+        if (ctx->plans.size() > 4096 && !stream_is_capturing(ctx)) clear_plans(ctx);
         CachedPlan cp;
         cp.plan = std::move(fresh);
-        if (!cp.plan.tile_order.empty()) { // alias-aware launch order: lives on the device with the plan
+        const bool tables = !cp.plan.tile_order.empty() || !cp.plan.tile_desc.empty() || !cp.plan.orbit_items.empty();
+        if (tables) {
+            // plan tables live on the device with the plan.  Uploading them allocates and synchronises, which is illegal
+            // while the stream is being captured into a CUDA graph: say so instead of invalidating the capture.
             cudaSetDevice(ctx->device);
-            const size_t bytes = cp.plan.tile_order.size() * sizeof(int32_t);
-            cudaError_t e = cudaMalloc(&cp.dev_order, bytes);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(cp.dev_order, cp.plan.tile_order.data(), bytes, cudaMemcpyHostToDevice, ctx->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            if (e != cudaSuccess) return cuda_fail(ctx, e, "tile order upload");
+            if (stream_is_capturing(ctx))
+                return set_err(ctx, SB_E_UNSUPPORTED, "first call of this plan inside a CUDA-graph capture: run the call once outside the capture (plan tables are uploaded on the first call)");
+            // (a plain synchronous copy: nothing of this plan is in flight yet)
+            auto upload = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
+                cudaError_t e = cudaMalloc(dst, bytes);
+                if (e == cudaSuccess) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+                return e;
+            };
+            cudaError_t e = cudaSuccess;
+            if (!cp.plan.tile_order.empty()) e = upload(&cp.dev_order, cp.plan.tile_order.data(), cp.plan.tile_order.size() * sizeof(int32_t)); // alias-aware launch order
+            if (e == cudaSuccess && !cp.plan.tile_desc.empty()) e = upload(&cp.dev_desc, cp.plan.tile_desc.data(), cp.plan.tile_desc.size() * sizeof(TileDesc)); // per-tile records of the TMA path
+            if (e == cudaSuccess && !cp.plan.orbit_items.empty()) e = upload(&cp.dev_orbit, cp.plan.orbit_items.data(), cp.plan.orbit_items.size() * sizeof(OrbitItem)); // work items of the orbit kernel
+            if (e != cudaSuccess) { // nothing half-built stays behind
+                if (cp.dev_order) cudaFree(cp.dev_order);
+                if (cp.dev_desc) cudaFree(cp.dev_desc);
+                if (cp.dev_orbit) cudaFree(cp.dev_orbit);
+                return cuda_fail(ctx, e, "plan table upload");
+            }
             cp.plan.tile_order.clear();
             cp.plan.tile_order.shrink_to_fit();
-        }
-        if (!cp.plan.tile_desc.empty()) { // per-tile records of the TMA path
-            cudaSetDevice(ctx->device);
-            const size_t bytes = cp.plan.tile_desc.size() * sizeof(TileDesc);
-            cudaError_t e = cudaMalloc(&cp.dev_desc, bytes);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(cp.dev_desc, cp.plan.tile_desc.data(), bytes, cudaMemcpyHostToDevice, ctx->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            if (e != cudaSuccess) return cuda_fail(ctx, e, "tile descriptor upload");
             cp.plan.tile_desc.clear();
             cp.plan.tile_desc.shrink_to_fit();
-        }
-        if (!cp.plan.orbit_items.empty()) { // work items of the alias-fused orbit kernel
-            cudaSetDevice(ctx->device);
-            const size_t bytes = cp.plan.orbit_items.size() * sizeof(OrbitItem);
-            cudaError_t e = cudaMalloc(&cp.dev_orbit, bytes);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(cp.dev_orbit, cp.plan.orbit_items.data(), bytes, cudaMemcpyHostToDevice, ctx->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            if (e != cudaSuccess) return cuda_fail(ctx, e, "orbit item upload");
             cp.plan.orbit_items.clear();
             cp.plan.orbit_items.shrink_to_fit();
         }
@@ -508,7 +560,7 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc, const PeerLink *peer = nul
     }
     if (peer) {
         const bool can = plan.kind == PLAN_REDUCE && plan.red.nouttiles == 1 && plan.red.nout_tile <= PEER_MAX_OUT && plan.key.ct != C64 &&
-                         desc.dtype[0] == plan.key.ct && !std::getenv("SB_NO_FUSED_PEER");
+                         desc.dtype[0] == plan.key.ct && env_cache().fused_peer;
         *fused = can;
         if (!can) return SB_OK;
         plan.red.peer = *peer;
@@ -521,18 +573,18 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc, const PeerLink *peer = nul
     // (plans with an alias-fused orbit variant keep the in-kernel interpreter: the orbit kernel is bound by its memory
     //  request rate, not by instruction issue, and beats the generic kernel + JIT by 2-3x on aliased views)
     if (plan.key.recipe == RC_INTERP && jit_enabled() && !(plan.kind == PLAN_MAP && plan.orbit_ok)) {
-        static const int64_t jit_min = []() {
-            const char *e = std::getenv("SB_JIT_MIN_ELEMENTS");
-            return e ? (int64_t)std::atoll(e) : ((int64_t)1 << 20);
-        }();
-        const char *e2 = std::getenv("SB_JIT_MIN_ELEMENTS"); // re-read: tests toggle it at run time
-        const int64_t thr = e2 ? (int64_t)std::atoll(e2) : jit_min;
+        const int64_t thr = (int64_t)env_cache().jit_min_elements;
         if (plan.elements >= thr)
-            jk = jit_get(plan.kind == PLAN_MAP ? JIT_MAP : JIT_REDUCE, plan.key, plan.kind == PLAN_MAP ? plan.map.prog : plan.red.prog);
+            jk = jit_get(plan.kind == PLAN_MAP ? JIT_MAP : JIT_REDUCE, plan.key, plan.kind == PLAN_MAP ? plan.map.prog : plan.red.prog,
+                         env_cache().jit_sync || plan.needs_jit);
+    }
+    if (plan.needs_jit) { // expression tree deeper than the interpreter's register stack: straight-line NVRTC code only, at any size
+        if (!jk && jit_enabled()) jk = jit_get(plan.kind == PLAN_MAP ? JIT_MAP : JIT_REDUCE, plan.key, plan.kind == PLAN_MAP ? plan.map.prog : plan.red.prog, true);
+        if (!jk) return set_err(ctx, SB_E_UNSUPPORTED, "program stack deeper than 4 needs the NVRTC-specialised kernel, which is unavailable (SB_NO_JIT / no libnvrtc)");
     }
     if (jk && plan.kind == PLAN_MAP) {
         const void *fn = (const void *)jk->fn;
-        if (plan.smem_bytes > 48 * 1024 && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes) != cudaSuccess) {
+        if (plan.smem_bytes > 48 * 1024 && ensure_dynamic_smem(fn, (size_t)plan.smem_bytes) != cudaSuccess) {
             cudaGetLastError();
             jk = nullptr;
         }
@@ -615,6 +667,8 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc, const PeerLink *peer = nul
         size_t scratch_need = plan.red.nsplit > 1 ? counters_bytes + (size_t)plan.scratch_bytes : 0;
         if (plan.stream_ok) scratch_need = std::max(scratch_need, counters_bytes + (size_t)plan.stream_grid * (size_t)plan.stream.nout * 16);
         if (scratch_need > ctx->scratch_bytes) {
+            if (stream_is_capturing(ctx))
+                return set_err(ctx, SB_E_UNSUPPORTED, "the reduction scratch buffer has to grow inside a CUDA-graph capture: run the call once outside the capture");
             if (ctx->scratch) {
                 cudaStreamSynchronize(ctx->stream);
                 cudaFree(ctx->scratch);

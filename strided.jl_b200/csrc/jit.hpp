@@ -20,8 +20,9 @@ struct JitKernel {
 
 enum JitKind : int { JIT_MAP = 0, JIT_REDUCE = 1 };
 
-// nullptr: JIT unavailable / failed for this key (the reason is kept in jit_last_log()).
-const JitKernel *jit_get(int kind, const KernelKey &key, const Program &prog);
+// nullptr: JIT unavailable / failed for this key (the reason is kept in jit_last_log()) -- or, with wait == false, still
+// being compiled on a worker thread (the caller runs the interpreter meanwhile and asks again on its next call).
+const JitKernel *jit_get(int kind, const KernelKey &key, const Program &prog, bool wait);
 const char *jit_last_log();
 bool jit_enabled();
 

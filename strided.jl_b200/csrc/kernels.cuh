@@ -9,7 +9,20 @@
 namespace sb {
 
 // launch with programmatic stream serialisation (see common.hpp "PDL"); SB_NO_PDL=1 turns the attribute off
-inline bool pdl_enabled() { return std::getenv("SB_NO_PDL") == nullptr; } // (re-read per launch: tools toggle it at run time)
+// The environment is read when a context is created (and again on sb_ctx_reload_env), never on the launch path.
+struct EnvCache {
+    bool pdl = true;                       // SB_NO_PDL
+    bool fused_peer = true;                // SB_NO_FUSED_PEER
+    long long jit_min_elements = 1 << 20;  // SB_JIT_MIN_ELEMENTS
+    bool jit_sync = false;                 // SB_JIT_SYNC: block on the NVRTC compile instead of compiling in the background
+};
+EnvCache &env_cache();  // abi.cu
+void env_reload();      // abi.cu
+inline bool pdl_enabled() { return env_cache().pdl; }
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is sticky per (device, function): set it once, and again only when a
+// plan needs more than was ever requested (it used to run on every launch).
+cudaError_t ensure_dynamic_smem(const void *func, size_t smem); // abi.cu
 template <class... KArgs, class... Args>
 cudaError_t launch_pdl(void (*k)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args &&...args)
 {
@@ -62,7 +75,7 @@ template <class CT, int RC, int NIN, int EPT, bool U> struct MapLaunch {
     {
         auto k = map_tile_kernel<CT, RC, NIN, EPT, U>;
         if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = ensure_dynamic_smem((const void *)k, smem);
             if (e != cudaSuccess) return e;
         }
         return launch_pdl(k, grid, THREADS, smem, s, P);
@@ -71,7 +84,7 @@ template <class CT, int RC, int NIN, int EPT, bool U> struct MapLaunch {
     {
         auto k = map_tile_kernel<CT, RC, NIN, EPT, U>;
         if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = ensure_dynamic_smem((const void *)k, smem);
             if (e != cudaSuccess) return e;
         }
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, THREADS, smem);
@@ -84,7 +97,7 @@ template <class AT, int RC, int NIN, int EPT, bool U> struct ReduceLaunch {
     {
         auto k = reduce_tile_kernel<AT, RC, NIN, EPT, U>;
         if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = ensure_dynamic_smem((const void *)k, smem);
             if (e != cudaSuccess) return e;
         }
         return launch_pdl(k, grid, THREADS, smem, s, P);

@@ -205,14 +205,14 @@ template <class CT, int RC, int NIN, int EPT, int LOGT> struct OrbitLaunch {
     static cudaError_t launch(const OrbitParams &O, const CUtensorMap *maps, int grid, size_t smem, cudaStream_t s)
     {
         auto k = map_orbit_kernel<CT, RC, NIN, EPT, LOGT>;
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = ensure_dynamic_smem((const void *)k, smem);
         if (e != cudaSuccess) return e;
         return launch_pdl(k, grid, (1 << LOGT) + 32, smem, s, O, maps[0], maps[1]);
     }
     static cudaError_t occupancy(int *nb, size_t smem)
     {
         auto k = map_orbit_kernel<CT, RC, NIN, EPT, LOGT>;
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = ensure_dynamic_smem((const void *)k, smem);
         if (e != cudaSuccess) return e;
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, (1 << LOGT) + 32, smem);
     }

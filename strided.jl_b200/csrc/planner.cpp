@@ -28,6 +28,7 @@ struct Canon {
     Tok tok[MAXTOK];
     int ct = F64;
     int src[MAXO] = {0, 1, 2, 3, 4, 5, 6, 7}; // canonical operand -> sb_desc operand (plan cache re-binds bases)
+    int depth = 0;                            // operand-stack depth the program needs (the interpreter keeps 4 in registers)
 };
 
 int64_t iabs64(int64_t x) { return x < 0 ? -x : x; }
@@ -283,7 +284,11 @@ int canonicalise(const sb_desc &d, Canon &c, bool &noop, std::string &err)
         rc = check_program(c, err, depth);
         if (rc != SB_OK) return rc;
     }
-    if (depth > 4) { err = "program stack deeper than 4"; return SB_E_UNSUPPORTED; }
+    // The in-kernel interpreter keeps a 4-deep operand stack in registers; deeper expression trees (the reference has no
+    // limit, src/broadcast.jl:67-98) are legal here too but can only run through the NVRTC-specialised kernel, which is
+    // straight-line code without a stack: the plan is marked `needs_jit` and the launch fails with SB_E_UNSUPPORTED
+    // (-> CPU method) only where NVRTC is unavailable.
+    c.depth = depth;
     if (c.nops < 2) { // `out .= const`: give the functor a (never read) input so that a[0] exists
         c.base[1] = c.base[0];
         c.src[1] = 0;
@@ -1180,13 +1185,15 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan, const DeviceInf
     O.log_threads = logt;
     O.nitems = (int32_t)items.size();
     O.prog = prog;
-    if (const char *dbg = std::getenv("SB_DEBUG")) { // diagnostics only: results are WRONG with these
+#ifdef SB_DIAG // diagnostics build only (make DIAG=1, tools/): results are WRONG with these; not compiled into the product
+    if (const char *dbg = std::getenv("SB_DEBUG")) {
         if (std::strstr(dbg, "noload")) O.debug |= 1;
         if (std::strstr(dbg, "nostore")) O.debug |= 2;
         if (std::strstr(dbg, "nocompute")) O.debug |= 4;
         if (std::strstr(dbg, "nofence")) O.debug |= 8;
         if (std::strstr(dbg, "nobar")) O.debug |= 16;
     }
+#endif
     auto addr_image = [&](int v, uint32_t m) {
         uint32_t a = 0;
         for (int p = 0; p < B; ++p)
@@ -1494,10 +1501,13 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
     const int V = (uniform && esz < 16 && want_vec) ? 16 / esz : 1;
     const int vbits = (V > 1 && ept % V == 0) ? ilog2_ceil(V) : 0;
     P.vbits = vbits;
-    if (const char *dbg = std::getenv("SB_DEBUG")) { // diagnostics only (tools/): results are WRONG with these
+#ifdef SB_DIAG // diagnostics build only (make DIAG=1, tools/): results are WRONG with SB_DEBUG; not compiled into the product
+    if (const char *dbg = std::getenv("SB_DEBUG")) {
         if (std::strstr(dbg, "nostore")) P.uniform |= 0x100;
         if (std::strstr(dbg, "noload")) P.uniform |= 0x200;
     }
+    if (std::getenv("SB_TMA_NOPREFETCH")) P.uniform |= 0x400; // A/B switch: tile records loaded where they are used
+#endif
     auto aligned16 = [&](int k) {
         if (((uintptr_t)c.base[k] & 15u) != 0) return false;
         for (int i = 0; i < n; ++i)
@@ -1855,8 +1865,13 @@ int build_plan(const sb_desc &d, const DeviceInfo &dev, Plan &plan, std::string 
             return SB_E_UNSUPPORTED;
         }
     }
-    if (c.op == OP_NONE) return plan_map(c, dev, plan, err);
-    return plan_reduce(c, dev, plan, err);
+    rc = c.op == OP_NONE ? plan_map(c, dev, plan, err) : plan_reduce(c, dev, plan, err);
+    if (rc == SB_OK && c.depth > 4) {
+        if (plan.key.recipe != RC_INTERP) { err = "internal: deep program matched a recipe"; return SB_E_INVALID; }
+        plan.needs_jit = true;
+        plan.orbit_ok = plan.tma_ok = plan.stream_ok = false; // (those variants run the interpreter for RC_INTERP plans)
+    }
+    return rc;
 }
 
 std::string describe_plan(const Plan &p)
@@ -1872,6 +1887,7 @@ std::string describe_plan(const Plan &p)
     os << ",\"ct\":\"" << ctn[p.key.ct] << "\",\"recipe\":\"" << rcn[p.key.recipe] << "\",\"nin_t\":" << p.key.nin
        << ",\"ept\":" << p.key.ept << ",\"uniform\":" << p.key.uniform << ",\"grid\":" << p.grid
        << ",\"smem_bytes\":" << p.smem_bytes << ",\"elements\":" << p.elements;
+    if (p.needs_jit) os << ",\"needs_jit\":1";
     auto arr64 = [&](const char *name, const int64_t *v, int n) {
         os << ",\"" << name << "\":[";
         for (int i = 0; i < n; ++i) os << (i ? "," : "") << v[i];

@@ -67,6 +67,8 @@ struct Plan {
     StreamParams stream{};
     int64_t stream_grid = 0;
     int64_t stream_smem_bytes = 0;
+    // the program needs more than the interpreter's 4 stack slots: only the NVRTC-specialised kernel can run it
+    bool needs_jit = false;
     std::string note;
 };
 

@@ -133,7 +133,13 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) reduce_stream_kernel(const 
     const AT *sc = reinterpret_cast<const AT *>(P.scratch);
     for (int o = warp; o < nout; o += THREADS / 32) {
         AT r = red_neutral<AT>(P.op);
-        for (uint32_t i = (uint32_t)lane; i < grid; i += 32) r = red_apply<AT>(P.op, r, load_partial(sc + (size_t)o * grid + i));
+        for (uint32_t i0 = (uint32_t)lane; i0 < grid; i0 += 256) { // eight independent L2 loads in flight per lane, folded in CTA order
+            AT v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (i0 + 32u * u < grid) ? load_partial(sc + (size_t)o * grid + i0 + 32u * u) : red_neutral<AT>(P.op);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) r = red_apply<AT>(P.op, r, v[u]);
+        }
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) r = red_apply<AT>(P.op, r, shfl_xor_any(r, m));
         if (lane == 0) {
@@ -155,14 +161,8 @@ template <class AT, int RC, int NIN> struct StreamLaunch {
     static cudaError_t launch(const ReduceParams &P, const StreamParams &S, int grid, size_t smem, cudaStream_t s)
     {
         auto k = reduce_stream_kernel<AT, RC, NIN>;
-        static bool attr_set[64] = {false}; // (the attribute is per function and device, and sticky)
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (e != cudaSuccess) return e;
-            if (dev >= 0 && dev < 64) attr_set[dev] = true;
-        }
+        cudaError_t e = ensure_dynamic_smem((const void *)k, smem);
+        if (e != cudaSuccess) return e;
         return launch_pdl(k, grid, STREAM_THREADS, smem, s, P, S);
     }
     static const void *func() { return (const void *)reduce_stream_kernel<AT, RC, NIN>; }

@@ -169,12 +169,17 @@ map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaP
         // The tile records were written once, at plan creation: they are fetched BEFORE griddepcontrol.wait (and one tile
         // ahead afterwards), so that no dependent global load sits between the wait and the first TMA issue -- for the
         // one-wave configs (1000^2, 32^4) that round trip was ~0.6 us of a ~4 us launch.
+        const bool prefetch = !(P.uniform & 0x400);
         TileDesc td_next = {};
-        if (P.tile_desc && blockIdx.x < ntiles) td_next = P.tile_desc[blockIdx.x];
+        if (prefetch && P.tile_desc && blockIdx.x < ntiles) td_next = P.tile_desc[blockIdx.x];
         pdl_wait(); // the operands may be the previous kernel's output
         for (uint32_t pos = blockIdx.x; pos < ntiles; pos += grid) {
-            const TileDesc td = td_next;
-            if (P.tile_desc && pos + grid < ntiles) td_next = P.tile_desc[pos + grid];
+            TileDesc td = td_next;
+            if (prefetch) {
+                if (P.tile_desc && pos + grid < ntiles) td_next = P.tile_desc[pos + grid];
+            } else if (P.tile_desc) {
+                td = P.tile_desc[pos];
+            }
             mbar_wait(smem_u32(&empty_bar[stage]), parity);
             const uint32_t fb = smem_u32(&full_bar[stage]);
             if (lane == 0) mbar_expect_tx(fb, (uint32_t)T.stage_bytes);
@@ -217,14 +222,19 @@ map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaP
         tma_thread_init<NIN>(P, T, t, th);
         int stage = 0;
         uint32_t parity = 0;
+        const bool prefetch = !(P.uniform & 0x400);
         TileDesc td_next = {}; // (fetched before the wait and one tile ahead, see the producer)
-        if (P.tile_desc && blockIdx.x < ntiles) td_next = P.tile_desc[blockIdx.x];
+        if (prefetch && P.tile_desc && blockIdx.x < ntiles) td_next = P.tile_desc[blockIdx.x];
         pdl_wait(); // the output may still be read or written by the previous kernel
         for (uint32_t pos = blockIdx.x; pos < ntiles; pos += grid) {
             MapTile<1> tl;
             if (P.tile_desc) {
-                const TileDesc td = td_next;
-                if (pos + grid < ntiles) td_next = P.tile_desc[pos + grid];
+                TileDesc td = td_next;
+                if (prefetch) {
+                    if (pos + grid < ntiles) td_next = P.tile_desc[pos + grid];
+                } else {
+                    td = P.tile_desc[pos];
+                }
                 tl.id = td.id_full & 0x7fffffffu;
                 tl.full = (td.id_full >> 31) != 0;
                 tl.ptr[0] = P.base[0] + (td.out_off + th0.g_toff[0]);
@@ -254,14 +264,14 @@ template <class CT, int RC, int NIN, int EPT> struct TmaLaunch {
     static cudaError_t launch(const MapParams &P, const TmaParams &T, const CUtensorMap *maps, int grid, size_t smem, cudaStream_t s)
     {
         auto k = map_tma_kernel<CT, RC, NIN, EPT>;
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = ensure_dynamic_smem((const void *)k, smem);
         if (e != cudaSuccess) return e;
         return launch_pdl(k, grid, TMA_THREADS, smem, s, P, T, maps[0], maps[1], maps[2], maps[3]);
     }
     static cudaError_t occupancy(int *nb, size_t smem)
     {
         auto k = map_tma_kernel<CT, RC, NIN, EPT>;
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = ensure_dynamic_smem((const void *)k, smem);
         if (e != cudaSuccess) return e;
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, TMA_THREADS, smem);
     }

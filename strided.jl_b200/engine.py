@@ -52,6 +52,10 @@ class Engine:
         abi.check(self.lib, self.ctx, self.lib.sb_ctx_set_sync(self.ctx, 1 if sync else 0))
         self.sync = bool(sync)
 
+    def reload_env(self):
+        """SB_* knobs are read at ctx creation; call this after changing them (tests, tuning tools)."""
+        abi.check(self.lib, self.ctx, self.lib.sb_ctx_reload_env(self.ctx))
+
     def synchronize(self):
         abi.check(self.lib, self.ctx, self.lib.sb_sync(self.ctx))
 

@@ -363,6 +363,10 @@ extern "C" int emul_mapreduce(const sb_desc *desc, int grid_limit)
     int rc = build_plan(*desc, dev, plan, g_err);
     if (rc != SB_OK) return rc;
     if (plan.kind == PLAN_NOOP) return SB_OK;
+    if (plan.needs_jit) { // (the emulator runs the interpreter bodies; deep programs exist only as NVRTC kernels)
+        g_err = "emul: program needs the NVRTC path";
+        return SB_E_UNSUPPORTED;
+    }
     if (!plan.tile_order.empty()) plan.map.tile_order = plan.tile_order.data();
     bool ok = false;
     if (plan.kind == PLAN_MAP) {

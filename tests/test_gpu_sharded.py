@@ -101,6 +101,9 @@ def _check_fused(rank, world, device, loc2, A3, full):
     # fused one -- same wire format, same results
     if rank == 0:
         os.environ["SB_NO_FUSED_PEER"] = "1"
+        peers = eng.peer_world
+        eng.reload_env()  # (the SB_* knobs are read at ctx creation / on reload; the peer group survives)
+        assert eng.peer_world == peers
     launches0 = eng.stats()["launches"]
     out2 = sharded.sharded_mapreduce("abs2", "+", loc2, dims=(1, 2), shard_dim=2)
     assert eng.stats()["launches"] - launches0 == (2 if rank == 0 else 1)
@@ -108,6 +111,7 @@ def _check_fused(rank, world, device, loc2, A3, full):
     s2 = sharded.sharded_mapreduce("identity", "+", loc2, shard_dim=2)
     assert s2 == s
     os.environ.pop("SB_NO_FUSED_PEER", None)
+    eng.reload_env()
     eng.peer_detach()
 
 

@@ -371,6 +371,21 @@ int main(int argc, char **argv)
             report(NAME, grid, TH, U, tail, a, b);                                                                      \
         }                                                                                                               \
     }
+    const bool quick = argc > 2; // calibration run: only the best variant of each family
+    if (quick) {
+        P.tail = 1;
+        float a = time_graph([&](int i) { RP q = P; q.x = bufs[i % nbuf]; launch_pdl(k_ldg<512, 4>, sms * 4, 512, 0, s, q, true); }, R, s);
+        float b = time_graph([&](int i) { RP q = P; q.x = bufs[0]; launch_pdl(k_ldg<512, 4>, sms * 4, 512, 0, s, q, true); }, R, s);
+        report("ldg", sms * 4, 512, 4, 1, a, b);
+        const int chunk = 32768, stages = 4;
+        CK(cudaFuncSetAttribute(k_bulk<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, chunk * stages));
+        P.chunk_bytes = chunk;
+        P.stages = stages;
+        a = time_graph([&](int i) { RP q = P; q.x = bufs[i % nbuf]; launch_pdl(k_bulk<256>, sms, 288, (size_t)chunk * stages, s, q, true); }, R, s);
+        b = time_graph([&](int i) { RP q = P; q.x = bufs[0]; launch_pdl(k_bulk<256>, sms, 288, (size_t)chunk * stages, s, q, true); }, R, s);
+        report("bulk32k", sms, 256, stages, 1, a, b);
+        return 0;
+    }
     RUN_LDG(k_ldg, "ldg", 256, 4)
     RUN_LDG(k_ldg, "ldg", 256, 8)
     RUN_LDG(k_ldg, "ldg", 512, 4)
