@@ -222,7 +222,7 @@ def sharded_record(torch, sb, dist, eng, rank, world, dev, peak):
     ms = _graph_time(torch, step, 40, side, barrier)
     want = (slab.view(per, K * K) ** 2).sum(dim=1)
     assert torch.allclose(out, want, rtol=1e-12, atol=0.0), ("sharded C5: per-slice sums differ from torch", out, want)
-    plan = sb.plan_describe(sb.make_desc(prog, 1, 1, 0.0, (per, K, K), [O, A]))
+    from bench_configs import _kernel
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -233,7 +233,7 @@ def sharded_record(torch, sb, dist, eng, rank, world, dev, peak):
         "n_gpus": world, "slices_per_gpu": per, "scaling": "strong", "algorithmic_bytes": total_bytes,
         "us_per_step_max_over_ranks": ms * 1e3, "aggregate_GBps": total_bytes / (ms * 1e-3) / 1e9,
         "frac_of_N_x_peak": total_bytes / (ms * 1e-3) / 1e9 / (peak * world),
-        "kernel": f"{plan.get('family')}<f64, abs2, EPT={plan.get('ept')}> grid {plan.get('grid')}, nsplit {plan.get('nsplit')}",
+        "kernel": _kernel(prog, 1, 1, (per, K, K), [O, A]),
         "placement": "dense 4096x4096 slab per slice in each GPU's HBM; no data-path collective",
         "checked": "every out[g] against torch (rtol 1e-12) on every rank",
     }

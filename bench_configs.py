@@ -118,7 +118,14 @@ def run_all(eng, peak):
         out.append(_entry(f"C3 f64 {m}^4 permutedims (4,3,2,1) (rot)", 2 * m ** 4 * 8, ms, peak, sets=k, kernel=_kernel([], 0, 0, shape, list(pairs[0]))))
         ms = _time(lambda i: sb.copy_(*pairs[0]), 300)
         out.append(_entry(f"C3 f64 {m}^4 permutedims (4,3,2,1) (warm, L2-resident)", 2 * m ** 4 * 8, ms, peak))
-        del As, Bs, pairs
+        # eight independent problems of this size as ONE batch (sb_mapreduce_batch): the calls overlap on side streams /
+        # parallel graph branches instead of queueing behind each other's launch + DRAM latency; time PER PROBLEM
+        nb = 8
+        batches = [[([], 0, 0, 0.0, shape, list(pairs[(j * nb + q) % k])) for q in range(nb)] for j in range(max(1, k // nb))]
+        ms = _time(lambda i: sb.run_batch(batches[i % len(batches)]), 10 * len(batches)) / nb
+        out.append(_entry(f"C3 f64 {m}^4 permutedims (4,3,2,1) x{nb} in one batch (rot, per problem)", 2 * m ** 4 * 8, ms, peak, batch=nb,
+                          kernel="sb_mapreduce_batch: " + _kernel([], 0, 0, shape, list(pairs[0]))))
+        del As, Bs, pairs, batches
 
     # C4: F32 64^4 and C4': F64 32^4 4-way permutedims sum
     p4 = [A_(0), A_(1), CALL("add"), A_(2), CALL("add"), A_(3), CALL("add")]

@@ -153,6 +153,15 @@ int sb_memcpy_d2h(sb_ctx *ctx, void *dst, const void *src, size_t bytes);
  * device-resident operands.  Thread-safe per ctx. */
 int sb_mapreduce(sb_ctx *ctx, const sb_desc *desc);
 
+/* n calls as ONE batch (device pointers).  Small problems are bound by launch and DRAM latency (~4 us each on a B200,
+ * whatever the kernel does); the batch runs its INDEPENDENT map calls -- output byte range disjoint from every other
+ * call's operands -- concurrently on side streams between a fork and a join on the ctx's stream, everything else
+ * (reductions, chains such as B = f(A); C = g(B)) in order after the join.  Results are the same as n sb_mapreduce calls
+ * in order.  Capturable in a CUDA graph (parallel branches) once a batch has run outside the capture.  The reference
+ * issues one `_mapreduce_fuse!` per statement (src/mapreduce.jl:98); this is the entry a glue uses for a block of
+ * independent `@strided` statements. */
+int sb_mapreduce_batch(sb_ctx *ctx, int n, const sb_desc *descs);
+
 /* Same call for HOST-resident operands (plain Julia `Array` parents): stages every distinct parent
  * range to the device once (aliased views share one copy), runs sb_mapreduce, copies the output
  * range back.  This is the end-to-end entry `bench.py` times as "e2e".
@@ -210,6 +219,7 @@ typedef struct sb_stats {
     uint64_t plans_cached;
     uint64_t jit_launches; /* launches of NVRTC-specialised kernels (subset of `launches`) */
     uint64_t zero_copy_calls; /* sb_mapreduce_host calls served without staging (kernel reads/writes pinned host memory) */
+    uint64_t batches;         /* sb_mapreduce_batch calls */
 } sb_stats;
 int sb_get_stats(sb_ctx *ctx, sb_stats *out);
 int sb_reset_stats(sb_ctx *ctx);

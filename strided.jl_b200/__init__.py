@@ -13,7 +13,7 @@ from .view import StridedView, sreshape, sview, isstrided, maybestrided
 from .broadcast import (Broadcasted, Ref, Arg, materialize, materialize_, capturestridedargs, promoteshape,
                         make_program, trace, identity, neg, conj, abs_, abs2, real, imag, sqrt, exp, log, sin, cos,
                         tanh, inv, add, sub, mul, div, maximum2, minimum2, lt)
-from .engine import get_engine, make_desc, run_mapreduce, similar_parent
+from .engine import get_engine, make_desc, run_mapreduce, run_batch, similar_parent
 from .mapreduce import (map_, map, copy_, conj_, adjoint_, transpose_, permutedims_, mapreduce, mapreducedim_,
                         _mapreducedim_, sum, prod, maximum, minimum, rmul_, lmul_, mul_, axpy_, axpby_, mul_generic_, _mul_generic_call)
 

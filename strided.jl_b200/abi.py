@@ -54,7 +54,7 @@ class sb_desc(C.Structure):
 class sb_stats(C.Structure):
     _fields_ = [("launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("plans_built", C.c_uint64), ("plans_cached", C.c_uint64), ("jit_launches", C.c_uint64),
-                ("zero_copy_calls", C.c_uint64)]
+                ("zero_copy_calls", C.c_uint64), ("batches", C.c_uint64)]
 
 
 class StridedB200Error(RuntimeError):
@@ -77,7 +77,7 @@ class NoDeviceError(StridedB200Error):
 
 EXPORTS = [
     "sb_abi_version", "sb_ctx_create", "sb_ctx_destroy", "sb_ctx_set_stream", "sb_ctx_set_sync", "sb_ctx_reload_env", "sb_sync",
-    "sb_last_error", "sb_malloc", "sb_free", "sb_memcpy_h2d", "sb_memcpy_d2h", "sb_mapreduce",
+    "sb_last_error", "sb_malloc", "sb_free", "sb_memcpy_h2d", "sb_memcpy_d2h", "sb_mapreduce", "sb_mapreduce_batch",
     "sb_mapreduce_host", "sb_plan_describe", "sb_get_stats", "sb_reset_stats",
     "sb_peer_export", "sb_peer_attach", "sb_peer_detach", "sb_mapreduce_allreduce",
 ]
@@ -115,6 +115,7 @@ def load_library():
     lib.sb_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
     lib.sb_mapreduce.argtypes = [vp, C.POINTER(sb_desc)]
     lib.sb_mapreduce_host.argtypes = [vp, C.POINTER(sb_desc)]
+    lib.sb_mapreduce_batch.argtypes = [vp, i32, C.POINTER(sb_desc)]
     lib.sb_plan_describe.argtypes = [vp, C.POINTER(sb_desc), C.c_char_p, C.c_size_t]
     lib.sb_get_stats.argtypes = [vp, C.POINTER(sb_stats)]
     lib.sb_reset_stats.argtypes = [vp]

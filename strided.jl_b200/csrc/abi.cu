@@ -15,6 +15,7 @@
 #include <unordered_map>
 #include <vector>
 #include <algorithm>
+#include <array>
 
 using namespace sb;
 
@@ -196,6 +197,10 @@ struct sb_ctx {
     void *peer_local = nullptr;                  // this rank's buffer (cudaMalloc)
     void *peer_buf[SB_PEER_MAX_WORLD] = {nullptr}; // [g] = rank g's buffer as seen from this process
     void *peer_tmp = nullptr;                    // local partial (SB_PEER_MAX_OUT elements of up to 16 bytes)
+    // sb_mapreduce_batch: side streams between a fork and a join on `stream`
+    static constexpr int NSIDE = 8;
+    cudaStream_t side[NSIDE] = {nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {nullptr};
 };
 
 static bool stream_is_capturing(sb_ctx *ctx)
@@ -302,6 +307,11 @@ int sb_ctx_destroy(sb_ctx *ctx)
     sb_peer_detach(ctx);
     if (ctx->peer_local) cudaFree(ctx->peer_local);
     if (ctx->peer_tmp) cudaFree(ctx->peer_tmp);
+    for (int q = 0; q < sb_ctx::NSIDE; ++q) {
+        if (ctx->side[q]) cudaStreamDestroy(ctx->side[q]);
+        if (ctx->ev_join[q]) cudaEventDestroy(ctx->ev_join[q]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->peer_epoch_dev) cudaFree(ctx->peer_epoch_dev);
     if (ctx->peer_err_host) cudaFreeHost((void *)ctx->peer_err_host);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -558,6 +568,12 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc, const PeerLink *peer = nul
         plan.map.base[k] = (unsigned char *)desc.base[plan.base_src[k] < desc.nops ? plan.base_src[k] : 0];
         plan.red.base[k] = plan.map.base[k];
     }
+    if (plan.kind == PLAN_MAP && plan.map.shift_last && output_overlaps_inputs(desc)) {
+        // in-place update: elements must be computed exactly once -> masked edge tiles, LSU kernel (the per-tile records
+        // of the TMA variant were built for the shifted tiling)
+        plan.map.shift_last = 0;
+        plan.tma_ok = false;
+    }
     if (peer) {
         const bool can = plan.kind == PLAN_REDUCE && plan.red.nouttiles == 1 && plan.red.nout_tile <= PEER_MAX_OUT && plan.key.ct != C64 &&
                          desc.dtype[0] == plan.key.ct && env_cache().fused_peer;
@@ -690,7 +706,23 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc, const PeerLink *peer = nul
             for (int q = 1; q <= plan.stream.nin; ++q) aligned = aligned && (((uintptr_t)plan.red.base[q] & 15u) == 0);
             const StreamEntry *sk = aligned ? find_stream_kernel(plan.key) : nullptr;
             if (sk) {
-                e = sk->launch(plan.red, plan.stream, (int)plan.stream_grid, (size_t)plan.stream_smem_bytes, ctx->stream);
+                StreamArgs sa;
+                std::memset(&sa, 0, sizeof sa);
+                for (int q = 0; q <= plan.stream.nin; ++q) {
+                    sa.base[q] = plan.red.base[q];
+                    sa.dtype[q] = plan.red.dtype[q];
+                    sa.conj[q] = plan.red.conj[q];
+                }
+                sa.op = plan.red.op;
+                sa.initop = plan.red.initop;
+                sa.init_re = plan.red.init_re;
+                sa.init_im = plan.red.init_im;
+                sa.scratch = plan.red.scratch;
+                sa.counters = plan.red.counters;
+                sa.peer = plan.red.peer;
+                sa.S = plan.stream;
+                sa.prog = plan.red.prog;
+                e = sk->launch(sa, (int)plan.stream_grid, (size_t)plan.stream_smem_bytes, ctx->stream);
                 if (e != cudaSuccess) return cuda_fail(ctx, e, "reduce_stream launch");
                 ctx->stats.launches++;
                 return SB_OK;
@@ -720,6 +752,116 @@ extern "C" int sb_mapreduce(sb_ctx *ctx, const sb_desc *desc)
     if (ctx->sync) {
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) return cuda_fail(ctx, e, "kernel execution");
+    }
+    return SB_OK;
+}
+
+// ---- batches of independent calls ---------------------------------------------------------------------------------
+// Small problems (the README-sized shapes: 1000^2, 32^4) are bound by launch and DRAM latency, not by bandwidth: one after
+// the other they cost ~4 us each whatever the kernel does.  A batch spreads its INDEPENDENT map calls over side streams
+// between a fork and a join on the ctx's stream, so they overlap; under stream capture this becomes parallel branches of
+// the CUDA graph.  A call is independent when it is a map whose output byte range overlaps no other call's operands; all
+// other calls (reductions share the ctx's scratch; chains such as B = f(A); C = g(B)) run in order after the join.
+static void desc_ranges(const sb_desc &d, uintptr_t (&lo)[SB_MAX_OPS], uintptr_t (&hi)[SB_MAX_OPS])
+{
+    for (int k = 0; k < d.nops && k < SB_MAX_OPS; ++k) {
+        int64_t l, h;
+        operand_range(d, k, l, h);
+        lo[k] = (uintptr_t)d.base[k] + (uintptr_t)l;
+        hi[k] = (uintptr_t)d.base[k] + (uintptr_t)h;
+    }
+}
+
+extern "C" int sb_mapreduce_batch(sb_ctx *ctx, int n, const sb_desc *descs)
+{
+    if (!ctx) return set_err(nullptr, SB_E_INVALID, "sb_mapreduce_batch: null ctx");
+    if (n < 0 || (n > 0 && !descs)) return set_err(ctx, SB_E_INVALID, "sb_mapreduce_batch: bad arguments");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaSetDevice(ctx->device);
+    std::vector<char> parallel((size_t)n, 0);
+    {
+        std::vector<std::array<uintptr_t, SB_MAX_OPS>> lo((size_t)n), hi((size_t)n);
+        std::vector<char> sane((size_t)n, 0);
+        for (int i = 0; i < n; ++i) {
+            const sb_desc &d = descs[i];
+            sane[i] = d.ndim >= 0 && d.ndim <= SB_MAX_DIMS && d.nops >= 1 && d.nops <= SB_MAX_OPS;
+            if (!sane[i]) continue;
+            bool empty = false;
+            for (int q = 0; q < d.ndim; ++q) empty |= d.dims[q] <= 0;
+            if (empty) { // (zero-size problems touch at most the output through initop: leave them on the main stream)
+                sane[i] = 0;
+                continue;
+            }
+            uintptr_t l[SB_MAX_OPS] = {0}, h[SB_MAX_OPS] = {0};
+            desc_ranges(d, l, h);
+            for (int k = 0; k < SB_MAX_OPS; ++k) {
+                lo[i][k] = l[k];
+                hi[i][k] = h[k];
+            }
+        }
+        for (int i = 0; i < n; ++i) {
+            if (!sane[i] || descs[i].op != SB_OP_NONE) continue;
+            bool indep = true;
+            for (int j = 0; j < n && indep; ++j) {
+                if (j == i) continue;
+                if (!sane[j]) { // unknown footprint: be conservative
+                    indep = false;
+                    break;
+                }
+                auto overlap = [&](int a, int ka, int b, int kb) { return lo[a][ka] < hi[b][kb] && lo[b][kb] < hi[a][ka]; };
+                for (int k = 0; k < descs[j].nops && indep; ++k)
+                    if (overlap(i, 0, j, k)) indep = false; // my output against every operand of j (write-write, j reads what I write)
+                for (int q = 1; q < descs[i].nops && indep; ++q)
+                    if (overlap(i, q, j, 0)) indep = false; // my inputs against j's output (I read what j writes)
+            }
+            parallel[i] = indep ? 1 : 0;
+        }
+    }
+    int npar = 0;
+    for (int i = 0; i < n; ++i) npar += parallel[i];
+    cudaStream_t main_stream = ctx->stream;
+    int used = 0;
+    if (npar >= 2) {
+        used = npar < sb_ctx::NSIDE ? npar : sb_ctx::NSIDE;
+        for (int q = 0; q < used; ++q) {
+            if (!ctx->side[q]) {
+                if (stream_is_capturing(ctx)) return set_err(ctx, SB_E_UNSUPPORTED, "first sb_mapreduce_batch inside a CUDA-graph capture: run a batch once outside the capture");
+                cudaError_t e = cudaStreamCreateWithFlags(&ctx->side[q], cudaStreamNonBlocking);
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join[q], cudaEventDisableTiming);
+                if (e != cudaSuccess) return cuda_fail(ctx, e, "batch side stream");
+            }
+        }
+        if (!ctx->ev_fork) {
+            cudaError_t e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "batch fork event");
+        }
+        cudaError_t e = cudaEventRecord(ctx->ev_fork, main_stream);
+        for (int q = 0; q < used && e == cudaSuccess; ++q) e = cudaStreamWaitEvent(ctx->side[q], ctx->ev_fork, 0);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "batch fork");
+        int slot = 0, rc = SB_OK;
+        for (int i = 0; i < n && rc == SB_OK; ++i) {
+            if (!parallel[i]) continue;
+            ctx->stream = ctx->side[slot % used];
+            ++slot;
+            rc = run_desc(ctx, descs[i]);
+        }
+        ctx->stream = main_stream;
+        for (int q = 0; q < used; ++q) { // always join, also on error: the side streams must not stay forked (capture!)
+            cudaError_t e2 = cudaEventRecord(ctx->ev_join[q], ctx->side[q]);
+            if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(main_stream, ctx->ev_join[q], 0);
+            if (e2 != cudaSuccess && rc == SB_OK) rc = cuda_fail(ctx, e2, "batch join");
+        }
+        if (rc != SB_OK) return rc;
+    }
+    for (int i = 0; i < n; ++i) {
+        if (npar >= 2 && parallel[i]) continue;
+        const int rc = run_desc(ctx, descs[i]);
+        if (rc != SB_OK) return rc;
+    }
+    ctx->stats.batches++;
+    if (ctx->sync) {
+        cudaError_t e = cudaStreamSynchronize(main_stream);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "sb_mapreduce_batch");
     }
     return SB_OK;
 }

@@ -168,6 +168,14 @@ struct MapParams {
     int32_t tile_b[MAXD]; // tile extent per canonical dim (1 for grid-only dims)
     int32_t ntile[MAXD];  // ceil(dims/tile_b)
     int32_t nfull[MAXD];  // dims/tile_b: tile coordinate c is an interior (unmasked) tile iff c < nfull
+    // Shifted last tile: along a dim whose extent is not a multiple of the (power-of-two) tile extent, the LAST tile starts
+    // at dims - tile_b instead of (ntile-1)*tile_b, i.e. it overlaps its neighbour by `excess` = ntile*tile_b - dims
+    // elements, which are simply computed twice (same inputs, same bits).  Every tile is then a full, unmasked tile: for
+    // odd extents (41^4: 70 % of the tiles touch an edge) the masked slow path disappears.  Only for maps whose output
+    // overlaps no input (decided at bind time; in-place updates keep the masked edge tiles).
+    int32_t excess[MAXD]; // 0: dim is tiled exactly or is shorter than one tile
+    int32_t shift_last;
+    int32_t pad_shift_;
     FastDiv tdiv[MAXD];   // division by ntile[d]
     int64_t tstep[MAXO][MAXD]; // BYTES per tile step along d: tile_b[d] * strides[k][d] * sizeof(elem k)
     uint8_t tdim[MAXTD];  // tile-dim slot -> canonical dim
@@ -256,8 +264,9 @@ constexpr int ORB_MAXG = 4;      // tiles (= parent blocks) per work item
 constexpr int ORB_MAXIN = 4;
 constexpr int ORB_MAXLOGT = 9;    // consumer threads: 2^8 (two CTAs per SM possible) or 2^9 (one big CTA per SM), + 1 producer warp
 struct OrbitItem {
-    int32_t ntile;
-    int32_t pad_;
+    int32_t ntile;  // output tiles computed by this work item
+    int32_t nblock; // parent blocks loaded for it (>= ntile: small problems split an orbit's tiles over several items,
+                    // each of which loads all the orbit's blocks, so that every SM gets work)
     int32_t pcrd[ORB_MAXG][TMA_MAXRANK]; // TMA coordinates (parent dim order) of parent block s
     int32_t ocrd[ORB_MAXG][TMA_MAXRANK]; // TMA coordinates (output dim order) of output tile m
     uint8_t slot[ORB_MAXG][ORB_MAXIN];   // input k of output tile m reads parent block slot[m][k]
@@ -379,6 +388,29 @@ struct StreamParams {
     int64_t kin_bytes[MAXIN][STREAM_MAXKD]; // byte stride of input k along kept dim d (multiple of 16)
     int64_t kout_bytes[STREAM_MAXKD];       // byte stride of the output along kept dim d
 };
+
+// Kernel parameter block of reduce_stream_kernel: only what the streamed reduction reads (~1.9 KB; the tile plan's
+// ReduceParams is 4.6 KB, and the launch cost of a graph node grows with the size of its parameter block).  Member
+// names follow ReduceParams so that the shared helpers (peer exchange, element functions) take either.
+struct StreamArgs {
+    unsigned char *base[4]; // 0: output, 1..3: inputs
+    uint8_t dtype[4];
+    uint8_t conj[4];
+    int32_t op, initop;
+    double init_re, init_im;
+    unsigned char *scratch; // CTA partials [nout][grid] of the accumulator type
+    uint32_t *counters;     // arrival counter
+    PeerLink peer;
+    StreamParams S;
+    Program prog;
+};
+
+// element origin of tile coordinate c along canonical dim d (see MapParams::excess)
+SB_HD int64_t map_tile_origin(const MapParams &P, int d, uint32_t c)
+{
+    const int64_t o = (int64_t)c * P.tile_b[d];
+    return (P.shift_last && P.excess[d] != 0 && (int32_t)c == P.ntile[d] - 1) ? o - P.excess[d] : o;
+}
 
 // ---- in-tile linear index of element (t, j) -----------------------------------------------------------------
 // V = 2^vbits consecutive elements of the traversal (16 bytes) belong to the same thread, so that global loads/

@@ -73,15 +73,16 @@ SB_D uint32_t peer_epoch_begin(const PeerLink &L)
     return 0u;
 #endif
 }
-template <class AT> SB_D AT peer_ll_exchange(const ReduceParams &P, int idx, AT p, uint32_t epoch);
+template <class AT, class PT> SB_D AT peer_ll_exchange(const PT &P, int idx, AT p, uint32_t epoch);
 template <class AT> SB_D AT peer_ll_allreduce(const ReduceParams &P, int o, AT p, uint32_t epoch)
 {
     int idx;
     if (!peer_logical_index(P, o, idx)) return p; // padding lane of the output tile: nothing is stored for it
-    return peer_ll_exchange<AT>(P, idx, p, epoch);
+    return peer_ll_exchange<AT, ReduceParams>(P, idx, p, epoch);
 }
-// `idx`: logical output index on the wire (kept dims in ascending |output stride|, first dim fastest)
-template <class AT> SB_D AT peer_ll_exchange(const ReduceParams &P, int idx, AT p, uint32_t epoch)
+// `idx`: logical output index on the wire (kept dims in ascending |output stride|, first dim fastest).
+// PT: ReduceParams or StreamArgs (members `peer` and `op`).
+template <class AT, class PT> SB_D AT peer_ll_exchange(const PT &P, int idx, AT p, uint32_t epoch)
 {
 #if defined(__CUDA_ARCH__)
     static_assert(sizeof(AT) <= 8, "the low-latency exchange carries 4- and 8-byte elements");

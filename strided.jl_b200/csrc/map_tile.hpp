@@ -73,10 +73,14 @@ template <int NOPS> SB_HD void map_tile_init(const MapParams &P, const MapThread
             uint32_t q, c;
             fast_divmod(P.tdiv[d], id, q, c);
             id = q;
-            full = full && ((int32_t)c < P.nfull[d]);
+            const bool shifted = P.shift_last && P.excess[d] != 0 && (int32_t)c == P.ntile[d] - 1; // last tile pulled back: full
+            full = full && (shifted || (int32_t)c < P.nfull[d]);
 #pragma unroll
             for (int k = 0; k < NOPS; ++k)
-                if (k < P.nops) off[k] += (int64_t)c * P.tstep[k][d];
+                if (k < P.nops) {
+                    off[k] += (int64_t)c * P.tstep[k][d];
+                    if (shifted) off[k] -= (int64_t)P.excess[d] * P.strides[k][d] * dtype_size(P.dtype[k]);
+                }
         }
     }
 #pragma unroll
@@ -92,7 +96,7 @@ SB_HD uint32_t map_tile_rem(const MapParams &P, uint32_t id)
         uint32_t q, c;
         fast_divmod(P.tdiv[d], id, q, c);
         id = q;
-        origin[d] = (int64_t)c * P.tile_b[d];
+        origin[d] = map_tile_origin(P, d, c);
     }
     int32_t rem[MAXTD];
     for (int i = 0; i < P.ntd; ++i) {

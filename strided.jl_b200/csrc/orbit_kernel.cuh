@@ -123,7 +123,7 @@ map_orbit_kernel(const __grid_constant__ OrbitParams O, const __grid_constant__ 
             a1 = b1;
             fetch(pos + 2 * grid, b0, b1);
             const OrbitItem *it = reinterpret_cast<const OrbitItem *>(d);
-            const int ntile = it->ntile;
+            const int ntile = it->nblock; // parent blocks of this item (>= its output tiles)
             const uint32_t fb = smem_u32(&full_bar[stage]);
             if (lane == 0) mbar_expect_tx(fb, (uint32_t)(ntile * O.tile_bytes)); // arrive (release) + transaction bytes
             else mbar_arrive(fb);                                                // arrive (release) of this lane's item words

@@ -959,7 +959,7 @@ bool orbit_tile_bits(const Canon &c, OrbitGeom &G)
 
 // Work items: the orbits of the tile grid under  c -> pb_1^-1(pb_k(c))  (pb_k: tile -> parent block of input k), in
 // launch order.  False when an orbit has more than ORB_MAXG tiles or the grid is too small / too large.
-bool orbit_items(const Canon &c, const OrbitGeom &G, std::vector<OrbitItem> &items, int &gmax)
+bool orbit_items(const Canon &c, const OrbitGeom &G, const DeviceInfo &dev, std::vector<OrbitItem> &items, int &gmax)
 {
     const int n = G.n, nin = G.nin, esz = G.esz;
     const int *tb = G.tb;
@@ -1045,6 +1045,7 @@ bool orbit_items(const Canon &c, const OrbitGeom &G, std::vector<OrbitItem> &ite
         OrbitItem it;
         std::memset(&it, 0, sizeof it);
         it.ntile = (int32_t)orb.size();
+        it.nblock = it.ntile;
         gmax = std::max(gmax, it.ntile);
         for (int m = 0; m < it.ntile; ++m) {
             int64_t cc[MAXD], nc[MAXD];
@@ -1066,6 +1067,32 @@ bool orbit_items(const Canon &c, const OrbitGeom &G, std::vector<OrbitItem> &ite
             }
         }
         items.push_back(it);
+    }
+    // One-wave problems (fewer orbits than SMs: the README's Float64 32^4 4-way sum has 70): the output tiles of an orbit
+    // are dealt out to 2 or 4 work items, each of which loads ALL the orbit's parent blocks (a few extra L2 reads) and
+    // computes its share of the tiles, so that (almost) every SM gets an item instead of half of them idling.
+    {
+        int f = 1;
+        while (f < 4 && f * 2 <= gmax && (int64_t)items.size() * f * 2 <= (int64_t)dev.sm_count) f *= 2;
+        if (f > 1) {
+            std::vector<OrbitItem> split;
+            for (const OrbitItem &it : items) {
+                const int parts = std::min(f, it.ntile);
+                for (int q = 0; q < parts; ++q) {
+                    const int m0 = it.ntile * q / parts, m1 = it.ntile * (q + 1) / parts;
+                    OrbitItem s2 = it; // same parent blocks (pcrd, nblock)
+                    s2.ntile = m1 - m0;
+                    for (int m = 0; m < ORB_MAXG; ++m) {
+                        const int src = m0 + m < it.ntile ? m0 + m : m0;
+                        std::memcpy(s2.ocrd[m], it.ocrd[src], sizeof s2.ocrd[m]);
+                        std::memcpy(s2.slot[m], it.slot[src], sizeof s2.slot[m]);
+                        s2.ooff[m] = it.ooff[src];
+                    }
+                    split.push_back(s2);
+                }
+            }
+            items.swap(split);
+        }
     }
     // Longest items first: the short orbits (tiles on a diagonal of the tile grid: fewer distinct images) go to the END of
     // the launch order, so that the CTAs that get one item more than the others in the last round get a short one
@@ -1167,7 +1194,7 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan, const DeviceInf
 
     std::vector<OrbitItem> items;
     int gmax = 1;
-    if (!orbit_items(c, G, items, gmax)) return false;
+    if (!orbit_items(c, G, dev, items, gmax)) return false;
 
     const int B = ebits, lg = esz == 4 ? 2 : 3;
     int ebit[ORB_MAXIN + 1][16];
@@ -1460,6 +1487,9 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
         P.nfull[i] = (int32_t)(c.dims[i] / P.tile_b[i]);
         P.tdiv[i] = make_fastdiv((uint32_t)nt);
         P.ntiles *= nt;
+        // shifted last tile (common.hpp MapParams::excess): only where the dim holds at least one whole tile
+        P.excess[i] = (P.tile_b[i] > 1 && c.dims[i] >= P.tile_b[i]) ? (int32_t)(nt * P.tile_b[i] - c.dims[i]) : 0;
+        if (P.excess[i] != 0 && !std::getenv("SB_NO_SHIFT")) P.shift_last = 1;
     }
     if (P.ntiles > 0x7fffffff) { err = "too many tiles"; return SB_E_UNSUPPORTED; }
     for (int i = 0; i < ntd; ++i) P.tdim[i] = (uint8_t)tdim[i];
@@ -1568,9 +1598,10 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
             for (int d = 0; d < n; ++d) {
                 const uint32_t cd = id % (uint32_t)P.ntile[d];
                 id /= (uint32_t)P.ntile[d];
-                td.origin[d] = (int32_t)cd * P.tile_b[d];
-                td.out_off += (int64_t)cd * P.tstep[0][d];
-                full = full && ((int32_t)cd < P.nfull[d]);
+                const bool shifted = P.shift_last && P.excess[d] != 0 && (int32_t)cd == P.ntile[d] - 1;
+                td.origin[d] = (int32_t)map_tile_origin(P, d, cd);
+                td.out_off += (int64_t)cd * P.tstep[0][d] - (shifted ? (int64_t)P.excess[d] * P.strides[0][d] * dtype_size(P.dtype[0]) : 0);
+                full = full && (shifted || (int32_t)cd < P.nfull[d]);
             }
             if (full) td.id_full |= 0x80000000u;
         }
@@ -1799,6 +1830,29 @@ int plan_reduce(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &
 
 } // namespace
 
+// Does the byte range of the output overlap the byte range of any input?  (in-place updates such as `Y .= a .* X .+ Y`)
+bool output_overlaps_inputs(const sb_desc &d)
+{
+    if (d.ndim < 0 || d.ndim > SB_MAX_DIMS || d.nops < 1 || d.nops > SB_MAX_OPS) return true;
+    uintptr_t lo[SB_MAX_OPS], hi[SB_MAX_OPS];
+    for (int k = 0; k < d.nops; ++k) {
+        if (d.dtype[k] < SB_F32 || d.dtype[k] > SB_C64) return true;
+        const int es = dtype_size(d.dtype[k]);
+        int64_t mn = 0, mx = 0;
+        for (int i = 0; i < d.ndim; ++i) {
+            if (d.dims[i] <= 0) return true;
+            const int64_t ext = (d.dims[i] - 1) * d.strides[k][i];
+            if (ext < 0) mn += ext;
+            else mx += ext;
+        }
+        lo[k] = (uintptr_t)d.base[k] + (uintptr_t)(mn * es);
+        hi[k] = (uintptr_t)d.base[k] + (uintptr_t)((mx + 1) * es);
+    }
+    for (int k = 1; k < d.nops; ++k)
+        if (lo[0] < hi[k] && lo[k] < hi[0]) return true;
+    return false;
+}
+
 // _mapreducedim! with a zero-size dim applies initop to a non-empty output (reference mapreduce.jl:88-91)
 bool empty_initop_desc(const sb_desc &D, sb_desc &E)
 {
@@ -1888,6 +1942,7 @@ std::string describe_plan(const Plan &p)
        << ",\"ept\":" << p.key.ept << ",\"uniform\":" << p.key.uniform << ",\"grid\":" << p.grid
        << ",\"smem_bytes\":" << p.smem_bytes << ",\"elements\":" << p.elements;
     if (p.needs_jit) os << ",\"needs_jit\":1";
+    if (p.kind == PLAN_MAP && p.map.shift_last) os << ",\"shift_last\":1";
     auto arr64 = [&](const char *name, const int64_t *v, int n) {
         os << ",\"" << name << "\":[";
         for (int i = 0; i < n; ++i) os << (i ? "," : "") << v[i];

@@ -79,6 +79,10 @@ int build_plan(const sb_desc &d, const DeviceInfo &dev, Plan &plan, std::string 
 // rewrites D into the equivalent `map!(initop, out, out)`; false when nothing has to be done.
 bool empty_initop_desc(const sb_desc &D, sb_desc &E);
 
+// true when the output's byte range overlaps an input's (or the descriptor is malformed): the shifted-last-tile plans
+// recompute a few elements and therefore need an output that no input aliases (decided per call, at bind time)
+bool output_overlaps_inputs(const sb_desc &d);
+
 // one-line JSON (sb_plan_describe)
 std::string describe_plan(const Plan &plan);
 

@@ -17,7 +17,7 @@ template <class AT> struct alignas(16) StreamVec {
 };
 
 template <class AT, int RC, int NIN, int OP>
-SB_HD void stream_fold_vec(const ReduceParams &P, const ElemFn<AT, RC> &fn, const StreamVec<AT> (&x)[NIN], AT &acc)
+SB_HD void stream_fold_vec(const StreamArgs &P, const ElemFn<AT, RC> &fn, const StreamVec<AT> (&x)[NIN], AT &acc)
 {
 #pragma unroll
     for (int u = 0; u < StreamVec<AT>::V; ++u) {
@@ -30,7 +30,7 @@ SB_HD void stream_fold_vec(const ReduceParams &P, const ElemFn<AT, RC> &fn, cons
 
 // one landed chunk: `stage` = base of the stage, `nv` = whole vectors in it (same for every input)
 template <class AT, int RC, int NIN, int OP>
-SB_HD void stream_chunk_op(const ReduceParams &P, const StreamParams &S, const unsigned char *stage, int nv, int t, AT (&acc)[STREAM_ACC])
+SB_HD void stream_chunk_op(const StreamArgs &P, const StreamParams &S, const unsigned char *stage, int nv, int t, AT (&acc)[STREAM_ACC])
 {
     ElemFn<AT, RC> fn;
     const StreamVec<AT> *in[NIN];
@@ -60,7 +60,7 @@ SB_HD void stream_chunk_op(const ReduceParams &P, const StreamParams &S, const u
 
 // (the reduction operator is dispatched once per chunk, not once per element)
 template <class AT, int RC, int NIN>
-SB_HD void stream_chunk(const ReduceParams &P, const StreamParams &S, const unsigned char *stage, int nv, int t, AT (&acc)[STREAM_ACC])
+SB_HD void stream_chunk(const StreamArgs &P, const StreamParams &S, const unsigned char *stage, int nv, int t, AT (&acc)[STREAM_ACC])
 {
     switch (P.op) {
     case OP_ADD: stream_chunk_op<AT, RC, NIN, OP_ADD>(P, S, stage, nv, t, acc); break;
@@ -86,7 +86,7 @@ SB_HD int64_t stream_out_offset(const StreamParams &S, int o, int k)
 }
 
 // the < 16-byte rest of output o's runs (elements [vec_bytes / sizeof(AT), nelem)), read straight from the operands
-template <class AT, int RC, int NIN> SB_HD AT stream_rest(const ReduceParams &P, const StreamParams &S, int o, AT acc)
+template <class AT, int RC, int NIN> SB_HD AT stream_rest(const StreamArgs &P, const StreamParams &S, int o, AT acc)
 {
     ElemFn<AT, RC> fn;
     for (int64_t e = S.vec_bytes / (int64_t)sizeof(AT); e < S.nelem; ++e) {
@@ -102,7 +102,7 @@ template <class AT, int RC, int NIN> SB_HD AT stream_rest(const ReduceParams &P,
 }
 
 // out[o] = op(initop(out[o]), total)   (reference src/mapreduce.jl:314 with the initop of :351-382)
-template <class AT> SB_HD void stream_store(const ReduceParams &P, const StreamParams &S, int o, AT total)
+template <class AT> SB_HD void stream_store(const StreamArgs &P, const StreamParams &S, int o, AT total)
 {
     unsigned char *dst = P.base[0] + stream_out_offset(S, o, -1);
     AT x = load_elem<AT, true>(dst, P.dtype[0], P.conj[0]);
@@ -111,7 +111,7 @@ template <class AT> SB_HD void stream_store(const ReduceParams &P, const StreamP
 }
 
 // the four accumulators of a thread, in slot order
-template <class AT> SB_HD AT stream_thread_total(const ReduceParams &P, const AT (&acc)[STREAM_ACC])
+template <class AT> SB_HD AT stream_thread_total(const StreamArgs &P, const AT (&acc)[STREAM_ACC])
 {
     AT p = acc[0];
 #pragma unroll

@@ -26,8 +26,9 @@ constexpr int STREAM_MAXSTAGE = 8;
 constexpr int STREAM_THREADS = THREADS + 32;
 
 template <class AT, int RC, int NIN>
-__global__ void __launch_bounds__(STREAM_THREADS, 1) reduce_stream_kernel(const __grid_constant__ ReduceParams P, const __grid_constant__ StreamParams S)
+__global__ void __launch_bounds__(STREAM_THREADS, 1) reduce_stream_kernel(const __grid_constant__ StreamArgs P)
 {
+    const StreamParams &S = P.S;
     extern __shared__ unsigned char sb_stream_smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STREAM_MAXSTAGE];
     __shared__ __align__(8) uint64_t empty_bar[STREAM_MAXSTAGE];
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) reduce_stream_kernel(const 
         for (int m = 16; m >= 1; m >>= 1) r = red_apply<AT>(P.op, r, shfl_xor_any(r, m));
         if (lane == 0) {
             if constexpr (sizeof(AT) <= 8) {
-                if (P.peer.world > 1) r = peer_ll_exchange<AT>(P, o, r, s_epoch); // one value per rank crosses NVLink, folded in rank order
+                if (P.peer.world > 1) r = peer_ll_exchange<AT, StreamArgs>(P, o, r, s_epoch); // one value per rank crosses NVLink, folded in rank order
             }
             stream_store<AT>(P, S, o, r);
         }
@@ -153,17 +154,17 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) reduce_stream_kernel(const 
 
 struct StreamEntry {
     KernelKey key; // (ct, recipe, nin); ept and uniform unused
-    cudaError_t (*launch)(const ReduceParams &, const StreamParams &, int grid, size_t smem, cudaStream_t);
+    cudaError_t (*launch)(const StreamArgs &, int grid, size_t smem, cudaStream_t);
     const void *func;
 };
 
 template <class AT, int RC, int NIN> struct StreamLaunch {
-    static cudaError_t launch(const ReduceParams &P, const StreamParams &S, int grid, size_t smem, cudaStream_t s)
+    static cudaError_t launch(const StreamArgs &P, int grid, size_t smem, cudaStream_t s)
     {
         auto k = reduce_stream_kernel<AT, RC, NIN>;
         cudaError_t e = ensure_dynamic_smem((const void *)k, smem);
         if (e != cudaSuccess) return e;
-        return launch_pdl(k, grid, STREAM_THREADS, smem, s, P, S);
+        return launch_pdl(k, grid, STREAM_THREADS, smem, s, P);
     }
     static const void *func() { return (const void *)reduce_stream_kernel<AT, RC, NIN>; }
 };

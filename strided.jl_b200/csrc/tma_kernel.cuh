@@ -89,7 +89,7 @@ __device__ __forceinline__ void tma_issue_box(const MapParams &P, const TmaOpera
             uint32_t qq, c;
             fast_divmod(P.tdiv[d], id, qq, c);
             id = qq;
-            const int32_t origin = (int32_t)c * P.tile_b[d];
+            const int32_t origin = (int32_t)map_tile_origin(P, d, c);
 #pragma unroll
             for (int i = 0; i < TMA_MAXRANK; ++i)
                 if (o.cdim[i] == d && i < o.rank) crd[i] = origin;
@@ -169,17 +169,16 @@ map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaP
         // The tile records were written once, at plan creation: they are fetched BEFORE griddepcontrol.wait (and one tile
         // ahead afterwards), so that no dependent global load sits between the wait and the first TMA issue -- for the
         // one-wave configs (1000^2, 32^4) that round trip was ~0.6 us of a ~4 us launch.
-        const bool prefetch = !(P.uniform & 0x400);
-        TileDesc td_next = {};
-        if (prefetch && P.tile_desc && blockIdx.x < ntiles) td_next = P.tile_desc[blockIdx.x];
+        // The tile records were written once, at plan creation: the FIRST one is fetched before griddepcontrol.wait, so that
+        // no dependent global load sits between the wait and the first TMA issue -- for the one-wave configs (1000^2, 32^4)
+        // that round trip was ~0.6 us of a ~4 us launch.  Later records are loaded where they are used, AFTER the stage
+        // has been freed: fetching them earlier (one tile ahead, or before the empty-barrier wait) makes the producer issue
+        // sooner and costs config 2 10 % (47.6 vs 42.7 us, profiles/r02_tma_prefetch_bisect.txt) -- the alias-aware tile
+        // order relies on the A and A' tiles of neighbouring CTAs meeting in L2, and that pacing is part of it.
+        TileDesc td_first = {};
+        if (P.tile_desc && blockIdx.x < ntiles) td_first = P.tile_desc[blockIdx.x];
         pdl_wait(); // the operands may be the previous kernel's output
         for (uint32_t pos = blockIdx.x; pos < ntiles; pos += grid) {
-            TileDesc td = td_next;
-            if (prefetch) {
-                if (P.tile_desc && pos + grid < ntiles) td_next = P.tile_desc[pos + grid];
-            } else if (P.tile_desc) {
-                td = P.tile_desc[pos];
-            }
             mbar_wait(smem_u32(&empty_bar[stage]), parity);
             const uint32_t fb = smem_u32(&full_bar[stage]);
             if (lane == 0) mbar_expect_tx(fb, (uint32_t)T.stage_bytes);
@@ -189,6 +188,8 @@ map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaP
             } else if (bk >= 0) {
                 const uint32_t dst = ring_u32 + (uint32_t)(stage * T.stage_bytes) + box_dst;
                 if (P.tile_desc) { // precomputed tile record: coordinates are a per-lane permutation of the origins
+                    TileDesc td = td_first;
+                    if (pos != blockIdx.x) td = P.tile_desc[pos];
                     int32_t crd[TMA_MAXRANK];
 #pragma unroll
                     for (int i = 0; i < TMA_MAXRANK; ++i) {
@@ -222,19 +223,14 @@ map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaP
         tma_thread_init<NIN>(P, T, t, th);
         int stage = 0;
         uint32_t parity = 0;
-        const bool prefetch = !(P.uniform & 0x400);
-        TileDesc td_next = {}; // (fetched before the wait and one tile ahead, see the producer)
-        if (prefetch && P.tile_desc && blockIdx.x < ntiles) td_next = P.tile_desc[blockIdx.x];
+        TileDesc td_first = {}; // (first record fetched before the wait, see the producer)
+        if (P.tile_desc && blockIdx.x < ntiles) td_first = P.tile_desc[blockIdx.x];
         pdl_wait(); // the output may still be read or written by the previous kernel
         for (uint32_t pos = blockIdx.x; pos < ntiles; pos += grid) {
             MapTile<1> tl;
             if (P.tile_desc) {
-                TileDesc td = td_next;
-                if (prefetch) {
-                    if (pos + grid < ntiles) td_next = P.tile_desc[pos + grid];
-                } else {
-                    td = P.tile_desc[pos];
-                }
+                TileDesc td = td_first;
+                if (pos != blockIdx.x) td = P.tile_desc[pos];
                 tl.id = td.id_full & 0x7fffffffu;
                 tl.full = (td.id_full >> 31) != 0;
                 tl.ptr[0] = P.base[0] + (td.out_off + th0.g_toff[0]);

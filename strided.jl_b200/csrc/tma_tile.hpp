@@ -118,7 +118,7 @@ SB_HD void tma_box_coords(const MapParams &P, const TmaOperand &o, uint32_t id, 
         uint32_t qq, c;
         fast_divmod(P.tdiv[d], id, qq, c);
         id = qq;
-        origin[d] = (int32_t)c * P.tile_b[d];
+        origin[d] = (int32_t)map_tile_origin(P, d, c);
     }
     for (int i = 0; i < TMA_MAXRANK; ++i) crd[i] = (i < o.rank) ? origin[o.cdim[i]] : 0;
     crd[0] += q * o.inner_step;

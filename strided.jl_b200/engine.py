@@ -86,6 +86,11 @@ class Engine:
     def mapreduce_allreduce(self, desc: abi.sb_desc):
         abi.check(self.lib, self.ctx, self.lib.sb_mapreduce_allreduce(self.ctx, C.byref(desc)))
 
+    def mapreduce_batch(self, descs):
+        """sb_mapreduce_batch: independent map calls overlap on side streams (device pointers)"""
+        arr = (abi.sb_desc * len(descs))(*descs)
+        abi.check(self.lib, self.ctx, self.lib.sb_mapreduce_batch(self.ctx, len(descs), arr))
+
     def mapreduce(self, desc: abi.sb_desc, host: bool):
         fn = self.lib.sb_mapreduce_host if host else self.lib.sb_mapreduce
         abi.check(self.lib, self.ctx, fn(self.ctx, C.byref(desc)))
@@ -150,6 +155,23 @@ def run_mapreduce(tokens, op, initop, init, dims, views, engine=None, allreduce=
         eng = engine or get_engine(0)
         eng.mapreduce(desc, host=True)
     return views[0]
+
+
+def run_batch(calls, engine=None):
+    """A block of `_mapreduce_fuse!` calls as ONE batch: `calls` = [(tokens, op, initop, init, dims, views), ...] on device
+    operands.  Independent map calls overlap (include/strided_b200.h: sb_mapreduce_batch); results are those of running the
+    calls in order."""
+    descs = [make_desc(*c) for c in calls]
+    devs = {v.device for c in calls for v in c[5]}
+    if len(devs) != 1 or not next(iter(devs)).startswith("cuda"):
+        raise ValueError("run_batch needs device-resident operands on one GPU")
+    dev = devs.pop()
+    idx = int(dev.split(":")[1]) if ":" in dev else torch.cuda.current_device()
+    eng = engine or get_engine(idx)
+    if engine is None:
+        eng.set_stream(torch.cuda.current_stream(idx).cuda_stream)
+    eng.mapreduce_batch(descs)
+    return [c[5][0] for c in calls]
 
 
 def similar_parent(like: StridedView, dtype_code: int, shape):

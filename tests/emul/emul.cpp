@@ -135,7 +135,7 @@ template <class CT, int RC, int NIN, int EPT> static void run_orbit(const Plan &
         for (uint32_t pos = (uint32_t)b; pos < (uint32_t)O.nitems; pos += (uint32_t)grid) {
             const OrbitItem &it = plan.orbit_items[pos];
             std::memset(ring.data() + (size_t)stage * O.stage_bytes, 0xCD, (size_t)O.stage_bytes);
-            for (int s = 0; s < it.ntile; ++s)
+            for (int s = 0; s < it.nblock; ++s)
                 emul_box(plan.orbit_global[0], it.pcrd[s], plan.map.base[1], ring.data() + (size_t)stage * O.stage_bytes + (size_t)s * O.tile_bytes, false);
             for (int m = 0; m < it.ntile; ++m) {
                 uint32_t slots;
@@ -227,7 +227,7 @@ template <class AT, int RC, int NIN, int EPT, bool U> static void run_reduce(con
 // Streamed complete reduction: the cp.async.bulk chunk copies are emulated (plain copies of the chunk of every input into
 // the stage), the real consumer body runs per thread; warp butterfly, CTA fold, partials and the last-CTA fold follow
 // the kernel's order (csrc/stream_kernel.cuh).
-template <class AT> static AT butterfly(const ReduceParams &P, AT *p)
+template <class AT, class PT> static AT butterfly(const PT &P, AT *p)
 {
     for (int m = 16; m >= 1; m >>= 1) {
         AT q[32];
@@ -238,8 +238,20 @@ template <class AT> static AT butterfly(const ReduceParams &P, AT *p)
 }
 template <class AT, int RC, int NIN> static void run_stream(const Plan &plan)
 {
-    const ReduceParams &P = plan.red;
-    const StreamParams &S = plan.stream;
+    StreamArgs P; // the lean parameter block the launch builds (csrc/abi.cu)
+    std::memset(&P, 0, sizeof P);
+    for (int q = 0; q <= plan.stream.nin; ++q) {
+        P.base[q] = plan.red.base[q];
+        P.dtype[q] = plan.red.dtype[q];
+        P.conj[q] = plan.red.conj[q];
+    }
+    P.op = plan.red.op;
+    P.initop = plan.red.initop;
+    P.init_re = plan.red.init_re;
+    P.init_im = plan.red.init_im;
+    P.S = plan.stream;
+    P.prog = plan.red.prog;
+    const StreamParams &S = P.S;
     const int grid = (int)plan.stream_grid;
     std::vector<unsigned char> raw((size_t)S.stage_bytes + 64);
     unsigned char *stage = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(raw.data()) + 15) & ~(uintptr_t)15);
@@ -268,7 +280,7 @@ template <class AT, int RC, int NIN> static void run_stream(const Plan &plan)
                     p[lane] = stream_thread_total<AT>(P, acc[t]);
                     if (b == 0 && t == 0) p[lane] = stream_rest<AT, RC, NIN>(P, S, o, p[lane]);
                 }
-                wres[w] = butterfly<AT>(P, p);
+                wres[w] = butterfly<AT, StreamArgs>(P, p);
             }
             AT q = wres[0];
             for (int w = 1; w < THREADS / 32; ++w) q = red_apply<AT>(P.op, q, wres[w]);
@@ -282,7 +294,7 @@ template <class AT, int RC, int NIN> static void run_stream(const Plan &plan)
             for (int i = lane; i < grid; i += 32) r = red_apply<AT>(P.op, r, partials[(size_t)o * grid + i]);
             p[lane] = r;
         }
-        stream_store<AT>(P, S, o, butterfly<AT>(P, p));
+        stream_store<AT>(P, S, o, butterfly<AT, StreamArgs>(P, p));
     }
 }
 template <class AT> static bool stream_dispatch(const Plan &plan)
@@ -368,6 +380,10 @@ extern "C" int emul_mapreduce(const sb_desc *desc, int grid_limit)
         return SB_E_UNSUPPORTED;
     }
     if (!plan.tile_order.empty()) plan.map.tile_order = plan.tile_order.data();
+    if (plan.kind == PLAN_MAP && plan.map.shift_last && output_overlaps_inputs(*desc)) { // as the launch does (csrc/abi.cu)
+        plan.map.shift_last = 0;
+        plan.tma_ok = false;
+    }
     bool ok = false;
     if (plan.kind == PLAN_MAP) {
         int grid = (int)plan.grid;

@@ -1,0 +1,90 @@
+"""GPU suite: sb_mapreduce_batch -- a block of `_mapreduce_fuse!` calls issued as one batch (independent map calls overlap on
+side streams, everything else runs in order).  The results must be those of the same calls made one after the other."""
+import numpy as np
+import pytest
+
+from helpers import A, F, K, P_COPY, sb
+
+pytestmark = pytest.mark.gpu
+
+
+def _col(shape):
+    st, acc = [], 1
+    for s in shape:
+        st.append(acc)
+        acc *= s
+    return tuple(st)
+
+
+def _calls(dev, seed=3):
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    calls, checks = [], []
+    sh = (16, 16, 16, 16)
+    for i, p in enumerate([(3, 2, 1, 0), (1, 2, 3, 0), (2, 3, 0, 1), (0, 2, 1, 3), (3, 0, 2, 1), (1, 0, 3, 2)]):  # six independent permutes
+        a = torch.randn(16 ** 4, dtype=torch.float64, device=dev, generator=g)
+        b = torch.zeros_like(a)
+        calls.append((P_COPY, 0, 0, 0.0, sh, [sb.StridedView(b, sh, _col(sh)), sb.StridedView(a, sh, _col(sh)).permutedims(p)]))
+        q = tuple(3 - p[3 - d] for d in range(4))
+        checks.append((b, a.view(*sh).permute(*q).contiguous().view(-1)))
+    n = 300
+    x = torch.randn(n * n, dtype=torch.float64, device=dev, generator=g)
+    y, z = torch.zeros_like(x), torch.zeros_like(x)
+    X, Y, Z = (sb.StridedView(t, (n, n), (1, n)) for t in (x, y, z))
+    calls.append(([K(3), A(0), F("mul")], 0, 0, 0.0, (n, n), [Y, X.T]))             # Y = 3 X'          } a chain: must run in order
+    calls.append(([A(0), A(1), F("add")], 0, 0, 0.0, (n, n), [Z, Y, X]))            # Z = Y + X         }
+    checks.append((y, (3 * x.view(n, n)).t().contiguous().view(-1)))  # column-major flat of 3 X' == row-major flat of ... checked below via numpy
+    s = torch.zeros(1, dtype=torch.float64, device=dev)
+    calls.append(([A(0), F("abs2")], 1, 1, 0.0, (n, n), [sb.StridedView(s, (n, n), (0, 0)), X]))  # a reduction: after the join
+    return calls, checks, (x, y, z, s, n)
+
+
+def test_batch_equals_sequential():
+    import torch
+    dev = torch.device("cuda", 0)
+    eng = sb.get_engine(0)
+    calls, checks, (x, y, z, s, n) = _calls(dev)
+    eng.reset_stats()
+    sb.run_batch(calls)
+    torch.cuda.synchronize()
+    assert eng.stats()["batches"] == 1 and eng.stats()["launches"] == len(calls)
+    for got, want in checks[:6]:
+        assert torch.equal(got, want)
+    xm = x.cpu().numpy().reshape((n, n), order="F")
+    assert np.array_equal(y.cpu().numpy().reshape((n, n), order="F"), 3 * xm.T)
+    assert np.array_equal(z.cpu().numpy().reshape((n, n), order="F"), 3 * xm.T + xm)
+    np.testing.assert_allclose(s.item(), float((xm ** 2).sum()), rtol=1e-12)
+    # the same calls one by one give the same bits
+    outs = [c[5][0].parent.clone() for c in calls]
+    for c in calls:
+        c[5][0].parent.zero_()
+    for c in calls:
+        sb.run_mapreduce(*c)
+    torch.cuda.synchronize()
+    for c, o in zip(calls, outs):
+        assert torch.equal(c[5][0].parent, o)
+
+
+def test_batch_in_cuda_graph():
+    import torch
+    dev = torch.device("cuda", 0)
+    eng = sb.get_engine(0)
+    calls, checks, _ = _calls(dev, seed=5)
+    eng.set_sync(False)
+    side = torch.cuda.Stream()
+    try:
+        with torch.cuda.stream(side):
+            sb.run_batch(calls)  # plans, side streams and events exist before the capture
+            torch.cuda.synchronize()
+            for c in calls:
+                c[5][0].parent.zero_()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                sb.run_batch(calls)
+            g.replay()
+            torch.cuda.synchronize()
+        for got, want in checks[:6]:
+            assert torch.equal(got, want)
+    finally:
+        eng.set_sync(True)
