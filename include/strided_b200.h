@@ -68,7 +68,10 @@ typedef enum sb_status {
 /* element types of StridedView parents on this path (othertests.jl:2,18,47,69,110) */
 typedef enum sb_dtype { SB_F32 = 0, SB_F64 = 1, SB_C32 = 2, SB_C64 = 3 } sb_dtype;
 
-/* reduction operator `op`; the neutral elements are those of _init_reduction! (mapreduce.jl:182-187) */
+/* reduction operator `op`; the neutral elements are those of _init_reduction! (mapreduce.jl:182-187).
+ * `&` and `|` (mapreduce.jl:186-187) are deliberately absent: they reduce Bool arrays, and Bool is not a device eltype
+ * (sb_dtype); the glue keeps such calls on the reference's CPU method.  Predicate COUNTS (`count(x -> x < 0, A)`,
+ * othertests.jl:116) are on the device path: SB_FN_LT yields 0/1 in the array's eltype and the count is an SB_OP_ADD. */
 typedef enum sb_op { SB_OP_NONE = 0, SB_OP_ADD = 1, SB_OP_MUL = 2, SB_OP_MIN = 3, SB_OP_MAX = 4 } sb_op;
 
 /* `initop` flavours seen on the path (linalg.jl:145-158, othertests.jl:76-102) */
