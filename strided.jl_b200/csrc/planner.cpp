@@ -745,6 +745,10 @@ bool plan_tma(const Canon &c, const MapParams &P, const int *tdim, Plan &plan, c
         if (P.staged[k]) {
             const int ipb = 128 / esz;
             if (b < ipb || b % ipb != 0 || rows < 8) return false;
+            // a transposing operand with a single 128-byte row per box line (16 Float64 along its contiguous dim: what odd
+            // extents such as 70^4 end up with) is faster through the LSU kernel: 105 vs 141 us on the 70^4 reversal
+            // (profiles/r02_j_odd_extents_tma_vs_lsu_shift.txt); from 256-byte rows on the TMA ring wins (54^4: 33 vs 54 us)
+            if (b * esz < 256 && !std::getenv("SB_TMA_NARROW")) return false;
             o.swizzle = 1;
             o.nbox = b / ipb;
             o.inner_step = ipb;
@@ -1586,7 +1590,18 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
     if (plan.smem_bytes > 200 * 1024) { err = "staging buffers exceed shared memory"; return SB_E_UNSUPPORTED; }
     plan.grid = std::min<int64_t>(P.ntiles, (int64_t)dev.sm_count * dev.ctas_per_sm);
     if (build_tile_order(c, P, plan.tile_order)) plan.note = "alias-aware tile order";
-    if (plan_tma(c, P, tdim, plan, dev) && P.ntiles <= (1 << 20) && !std::getenv("SB_NO_TILE_DESC")) {
+    const bool tma = plan_tma(c, P, tdim, plan, dev);
+    if (tma) {
+        // The TMA unit clips edge boxes for free, so pulling the last tile back only pays while the recomputed part is
+        // small: 54^4 reversal, 10 of 54 columns twice: 35.3 us shifted vs 33.1 us masked; 4002^2: 45.6 vs 46.8 us.
+        bool any = false;
+        for (int i = 0; i < n; ++i) {
+            if (P.excess[i] != 0 && (int64_t)P.excess[i] * 100 > 15 * c.dims[i]) P.excess[i] = 0;
+            any = any || P.excess[i] != 0;
+        }
+        if (!any) P.shift_last = 0;
+    }
+    if (tma && P.ntiles <= (1 << 20) && !std::getenv("SB_NO_TILE_DESC")) {
         plan.tile_desc.resize((size_t)P.ntiles);
         for (int64_t pos = 0; pos < P.ntiles; ++pos) {
             uint32_t id = plan.tile_order.empty() ? (uint32_t)pos : (uint32_t)plan.tile_order[(size_t)pos];
