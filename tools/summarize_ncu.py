@@ -1,6 +1,7 @@
 """Summarise an `ncu --set full` report (read here, no GPU needed) into a small JSON under profiles/.
 
     python tools/summarize_ncu.py gpurun_out/prof_c2.ncu-rep profiles/c2_kernel_ncu.json
+    python tools/summarize_ncu.py gpurun_out/r02_ncu_stream_raw.csv profiles/r02_ncu_stream.json
 """
 import csv
 import io
@@ -17,12 +18,19 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum", "lts__t_requests_srcunit_tex.sum", "sm__cycles_elapsed.avg", "smsp__cycles_active.avg",
+        "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "sm__maximum_warps_per_active_cycle_pct"]
 
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):  # `ncu -i X.ncu-rep --page raw --csv` exported on the GPU box (gpurun brings back <= 64 MiB)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     kernels = []
