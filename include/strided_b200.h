@@ -33,8 +33,9 @@
  *     conjugated on load, and (operand 0) on store (ParentIndex get/setindex, mapreduce.jl:276-278).
  *
  * Element functions outside the pre-compiled recipes run either through an in-kernel interpreter or, for problems of
- * at least SB_JIT_MIN_ELEMENTS elements (default 2^20), through a kernel specialised at run time with NVRTC and
- * cached on disk (~/.cache/strided_b200); SB_NO_JIT=1 disables the latter.
+ * at least SB_JIT_MIN_ELEMENTS elements (default 2^18), through a kernel specialised at run time with NVRTC (compiled on a
+ * worker thread while the interpreter keeps serving the calls; SB_JIT_SYNC=1 blocks instead) and cached on disk
+ * (~/.cache/strided_b200, private to the user); SB_NO_JIT=1 disables the latter.
  *
  * Error behaviour: no entry point throws or aborts; every one returns an `sb_status`.  The glue maps
  * SB_E_SHAPE -> DimensionMismatch (mapreduce.jl:43-46, broadcast.jl:61), SB_E_UNSUPPORTED -> fall

@@ -66,7 +66,7 @@ void env_reload()
     c.pdl = std::getenv("SB_NO_PDL") == nullptr;
     c.fused_peer = std::getenv("SB_NO_FUSED_PEER") == nullptr;
     const char *e = std::getenv("SB_JIT_MIN_ELEMENTS");
-    c.jit_min_elements = e ? std::atoll(e) : (1ll << 20);
+    c.jit_min_elements = e ? std::atoll(e) : (1ll << 18);
     c.jit_sync = std::getenv("SB_JIT_SYNC") != nullptr;
 }
 cudaError_t ensure_dynamic_smem(const void *func, size_t smem)

@@ -13,7 +13,7 @@ namespace sb {
 struct EnvCache {
     bool pdl = true;                       // SB_NO_PDL
     bool fused_peer = true;                // SB_NO_FUSED_PEER
-    long long jit_min_elements = 1 << 20;  // SB_JIT_MIN_ELEMENTS
+    long long jit_min_elements = 1 << 18;  // SB_JIT_MIN_ELEMENTS
     bool jit_sync = false;                 // SB_JIT_SYNC: block on the NVRTC compile instead of compiling in the background
 };
 EnvCache &env_cache();  // abi.cu

@@ -1978,7 +1978,11 @@ std::string describe_plan(const Plan &p)
             arr32("tile", p.orbit_tile_b, P.ndim);
             os << "}";
         }
-        os << ",\"ntiles\":" << P.ntiles << ",\"tile_order\":" << (p.tile_order.empty() ? 0 : 1) << ",\"tma\":" << (p.tma_ok ? p.tma.nstage : 0) << ",\"nstaged\":" << P.nstaged << ",\"staged\":[";
+        os << ",\"ntiles\":" << P.ntiles << ",\"tile_order\":" << (p.tile_order.empty() ? 0 : 1) << ",\"tma\":" << (p.tma_ok ? p.tma.nstage : 0);
+        // (`grid` / `smem_bytes` above describe the generic map_tile launch; the TMA ring kernel, when it binds, runs
+        //  min(ntiles, SMs x resident CTAs) CTAs of 288 threads with this much dynamic shared memory)
+        if (p.tma_ok) os << ",\"tma_smem_bytes\":" << p.tma_smem_bytes << ",\"tma_threads\":288";
+        os << ",\"nstaged\":" << P.nstaged << ",\"staged\":[";
         for (int k = 0; k < P.nops; ++k) os << (k ? "," : "") << (int)P.staged[k];
         os << "],\"strides\":[";
         for (int k = 0; k < P.nops; ++k) {
