@@ -48,7 +48,11 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) reduce_stream_kernel(const 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+#ifdef SB_STREAM_CONSUMER_NOWAIT // (experiment, tools/ubench_stream_product.cu) only the producer waits for the previous grid
+    if (warp == THREADS / 32) pdl_wait();
+#else
     pdl_wait(); // operands, output, partials and the arrival counter may all be in use by the previous kernel
+#endif
     const int64_t nchunks = S.nchunks;
     const uint32_t grid = gridDim.x;
     const int nout = S.nout;

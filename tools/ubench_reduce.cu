@@ -314,6 +314,7 @@ template <class... A> static void launch_pdl(void (*k)(A...), int grid, int bloc
     CK(cudaLaunchKernelEx(&cfg, k, p));
 }
 
+#ifndef UBENCH_NO_MAIN
 int main(int argc, char **argv)
 {
     const long long n = argc > 1 ? atoll(argv[1]) : (1ll << 24);
@@ -417,3 +418,4 @@ int main(int argc, char **argv)
     }
     return 0;
 }
+#endif // UBENCH_NO_MAIN
