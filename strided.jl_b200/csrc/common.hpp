@@ -384,6 +384,13 @@ struct StreamParams {
     int32_t stage_bytes; // nin * chunk_bytes
     int32_t nout;        // outputs = product of kdims (1: complete reduction)
     int32_t nkd;         // kept dims
+    // Interleaved mode (inter_g > 0): the kept dim is the INNERMOST, contiguous dim of the inputs (column-major
+    // `mapreduce(f, op, A; dims=(2,3))`, BASELINE config 5 on one GPU): the whole input is ONE dense run in which element e
+    // belongs to output e mod K.  With K * sizeof(T) = inter_g * 16 bytes (a power of two <= 512) every 16-byte vector
+    // lane of thread t always meets the same output ((t mod inter_g) * V + lane), so the same ring serves it with one
+    // accumulator per lane and an epilogue that folds lanes of equal class.
+    int32_t inter_g;
+    int32_t pad_inter_;
     int64_t kdims[STREAM_MAXKD];
     int64_t kin_bytes[MAXIN][STREAM_MAXKD]; // byte stride of input k along kept dim d (multiple of 16)
     int64_t kout_bytes[STREAM_MAXKD];       // byte stride of the output along kept dim d

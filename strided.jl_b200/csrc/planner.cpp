@@ -1645,11 +1645,29 @@ void plan_stream(const Canon &c, const DeviceInfo &dev, bool uniform, Plan &plan
     const int nin = c.nops - 1, esz = dtype_size(c.ct);
     if (c.ndim != c.nkept + 1 || c.nkept > STREAM_MAXKD || !uniform || nin < 1 || nin > 3) return;
     const int r = c.nkept; // the (fused) reduced dim
-    for (int k = 1; k <= nin; ++k)
-        if (c.strides[k][r] != 1) return;
     if (!stream_instantiated(plan.key.ct, plan.key.recipe, plan.key.nin)) return;
     StreamParams &S = plan.stream;
     std::memset(&S, 0, sizeof S);
+    // interleaved mode: ONE kept dim that is the innermost, contiguous dim of every input, the reduced dim dense on top of
+    // it (column-major `mapreduce(f, op, A; dims=(2,3))`: BASELINE config 5 on one GPU)
+    if (c.nkept == 1 && !std::getenv("SB_NO_STREAM_INTER")) {
+        const int64_t K = c.dims[0], kb = K * esz;
+        bool ok = kb >= 16 && kb <= 512 && (kb & (kb - 1)) == 0 && K <= STREAM_MAXOUT;
+        for (int k = 1; k <= nin && ok; ++k) ok = c.strides[k][0] == 1 && c.strides[k][1] == K;
+        if (ok) {
+            S.inter_g = (int32_t)(kb / 16);
+            S.nkd = 1;
+            S.kdims[0] = K;
+            S.kout_bytes[0] = c.strides[0][0] * dtype_size(c.dtype[0]);
+            S.nout = (int32_t)K;
+            S.nelem = K * c.dims[1];
+            if (c.dims[1] > ((int64_t)1 << 56) / kb) return;
+            S.vec_bytes = S.nelem * esz; // a multiple of K * esz >= 16
+        }
+    }
+    if (S.inter_g == 0) {
+    for (int k = 1; k <= nin; ++k)
+        if (c.strides[k][r] != 1) return;
     int64_t nout = 1;
     S.nkd = c.nkept;
     for (int d = 0; d < c.nkept; ++d) {
@@ -1666,6 +1684,7 @@ void plan_stream(const Canon &c, const DeviceInfo &dev, bool uniform, Plan &plan
     S.nelem = c.dims[r];
     if (S.nelem > ((int64_t)1 << 56) / esz) return;
     S.vec_bytes = (S.nelem * esz) & ~(int64_t)15;
+    } // (dense runs)
     if (S.vec_bytes < 64 * 1024) return; // (one or two CTAs of the tiled kernel do as well below that)
     S.nin = nin;
     // chunk per input: 32 KB / nin at most (four stages of 32 KB keep ~19 MB in flight over 148 SMs), smaller when the
@@ -2000,7 +2019,7 @@ std::string describe_plan(const Plan &p)
            << ",\"nout_tile\":" << P.nout_tile << ",\"nred_tile\":" << P.nred_tile
            << ",\"warp_per_output\":" << P.warp_per_output << ",\"scratch_bytes\":" << p.scratch_bytes;
         if (p.stream_ok)
-            os << ",\"stream\":{\"grid\":" << p.stream_grid << ",\"nout\":" << p.stream.nout << ",\"chunk_bytes\":" << p.stream.chunk_bytes << ",\"nstage\":" << p.stream.nstage
+            os << ",\"stream\":{\"grid\":" << p.stream_grid << ",\"nout\":" << p.stream.nout << ",\"interleaved\":" << p.stream.inter_g << ",\"chunk_bytes\":" << p.stream.chunk_bytes << ",\"nstage\":" << p.stream.nstage
                << ",\"nchunks\":" << p.stream.nchunks << ",\"smem_bytes\":" << p.stream_smem_bytes << "}";
     }
     os << "}";

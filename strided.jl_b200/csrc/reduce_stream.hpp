@@ -17,20 +17,20 @@ template <class AT> struct alignas(16) StreamVec {
 };
 
 template <class AT, int RC, int NIN, int OP>
-SB_HD void stream_fold_vec(const StreamArgs &P, const ElemFn<AT, RC> &fn, const StreamVec<AT> (&x)[NIN], AT &acc)
+SB_HD void stream_fold_vec(const StreamArgs &P, const ElemFn<AT, RC> &fn, const StreamVec<AT> (&x)[NIN], AT (&acc)[StreamVec<AT>::V])
 {
 #pragma unroll
-    for (int u = 0; u < StreamVec<AT>::V; ++u) {
+    for (int u = 0; u < StreamVec<AT>::V; ++u) { // one accumulator per vector lane: in the interleaved mode the lanes are different outputs
         AT a[NIN];
 #pragma unroll
         for (int k = 0; k < NIN; ++k) a[k] = x[k].v[u];
-        acc = red_apply<AT>(OP, acc, fn.template eval<NIN>(P.prog, a)); // OP is a compile-time constant: the switch folds away
+        acc[u] = red_apply<AT>(OP, acc[u], fn.template eval<NIN>(P.prog, a)); // OP is a compile-time constant: the switch folds away
     }
 }
 
 // one landed chunk: `stage` = base of the stage, `nv` = whole vectors in it (same for every input)
 template <class AT, int RC, int NIN, int OP>
-SB_HD void stream_chunk_op(const StreamArgs &P, const StreamParams &S, const unsigned char *stage, int nv, int t, AT (&acc)[STREAM_ACC])
+SB_HD void stream_chunk_op(const StreamArgs &P, const StreamParams &S, const unsigned char *stage, int nv, int t, AT (&acc)[STREAM_ACC][StreamVec<AT>::V])
 {
     ElemFn<AT, RC> fn;
     const StreamVec<AT> *in[NIN];
@@ -60,7 +60,7 @@ SB_HD void stream_chunk_op(const StreamArgs &P, const StreamParams &S, const uns
 
 // (the reduction operator is dispatched once per chunk, not once per element)
 template <class AT, int RC, int NIN>
-SB_HD void stream_chunk(const StreamArgs &P, const StreamParams &S, const unsigned char *stage, int nv, int t, AT (&acc)[STREAM_ACC])
+SB_HD void stream_chunk(const StreamArgs &P, const StreamParams &S, const unsigned char *stage, int nv, int t, AT (&acc)[STREAM_ACC][StreamVec<AT>::V])
 {
     switch (P.op) {
     case OP_ADD: stream_chunk_op<AT, RC, NIN, OP_ADD>(P, S, stage, nv, t, acc); break;
@@ -110,13 +110,26 @@ template <class AT> SB_HD void stream_store(const StreamArgs &P, const StreamPar
     store_elem<AT, true>(dst, P.dtype[0], P.conj[0], red_apply<AT>(P.op, x, total));
 }
 
-// the four accumulators of a thread, in slot order
-template <class AT> SB_HD AT stream_thread_total(const StreamArgs &P, const AT (&acc)[STREAM_ACC])
+// the accumulators of a thread: dense mode -> one value (slots in order, then lanes in order)
+template <class AT> SB_HD AT stream_thread_total(const StreamArgs &P, const AT (&acc)[STREAM_ACC][StreamVec<AT>::V])
 {
-    AT p = acc[0];
+    AT p = red_neutral<AT>(P.op);
 #pragma unroll
-    for (int q = 1; q < STREAM_ACC; ++q) p = red_apply<AT>(P.op, p, acc[q]);
+    for (int u = 0; u < StreamVec<AT>::V; ++u) {
+        AT pu = acc[0][u];
+#pragma unroll
+        for (int q = 1; q < STREAM_ACC; ++q) pu = red_apply<AT>(P.op, pu, acc[q][u]);
+        p = u == 0 ? pu : red_apply<AT>(P.op, p, pu);
+    }
     return p;
+}
+// interleaved mode -> one value per vector lane u (output number (t mod G) * V + u)
+template <class AT> SB_HD AT stream_thread_lane_total(const StreamArgs &P, const AT (&acc)[STREAM_ACC][StreamVec<AT>::V], int u)
+{
+    AT pu = acc[0][u];
+#pragma unroll
+    for (int q = 1; q < STREAM_ACC; ++q) pu = red_apply<AT>(P.op, pu, acc[q][u]);
+    return pu;
 }
 
 } // namespace sb

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) reduce_stream_kernel(const 
     extern __shared__ unsigned char sb_stream_smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STREAM_MAXSTAGE];
     __shared__ __align__(8) uint64_t empty_bar[STREAM_MAXSTAGE];
-    __shared__ __align__(16) unsigned char fold_raw[2 * (THREADS / 32) * sizeof(AT)];
+    __shared__ __align__(16) unsigned char fold_raw[(THREADS / 32) * STREAM_MAXOUT * sizeof(AT)]; // [warp][output] (dense mode uses 2 x 8 entries)
     __shared__ unsigned int is_last, s_epoch;
     AT *fold = reinterpret_cast<AT *>(fold_raw);
     unsigned char *ring = sb_stream_smem_raw + ((0u - smem_u32(sb_stream_smem_raw)) & 127u);
@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) reduce_stream_kernel(const 
         if (lane == 0) {
             int stage = 0;
             uint32_t parity = 1; // a fresh barrier passes a wait on parity 1: every stage starts out empty
-            for (int o = 0; o < nout; ++o) {
+            const int nruns_p = S.inter_g > 0 ? 1 : nout; // interleaved mode: ONE run carries all outputs
+            for (int o = 0; o < nruns_p; ++o) {
                 const unsigned char *src[NIN];
 #pragma unroll
                 for (int k = 0; k < NIN; ++k) src[k] = P.base[(k < S.nin ? k : 0) + 1] + stream_out_offset(S, o, k < S.nin ? k : 0);
@@ -86,12 +87,16 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) reduce_stream_kernel(const 
         return;
     }
     // ---------------- consumers ----------------
+    constexpr int V = StreamVec<AT>::V;
     int stage = 0;
     uint32_t parity = 0;
-    for (int o = 0; o < nout; ++o) {
-        AT acc[STREAM_ACC];
+    const int nruns = S.inter_g > 0 ? 1 : nout; // interleaved mode: ONE run carries all outputs
+    for (int o = 0; o < nruns; ++o) {
+        AT acc[STREAM_ACC][V];
 #pragma unroll
-        for (int q = 0; q < STREAM_ACC; ++q) acc[q] = red_neutral<AT>(P.op);
+        for (int q = 0; q < STREAM_ACC; ++q)
+#pragma unroll
+            for (int u = 0; u < V; ++u) acc[q][u] = red_neutral<AT>(P.op);
         for (int64_t c = blockIdx.x; c < nchunks; c += grid) {
             const int64_t left = S.vec_bytes - c * (int64_t)S.chunk_bytes;
             const int nv = (int)((left < (int64_t)S.chunk_bytes ? left : (int64_t)S.chunk_bytes) >> 4);
@@ -103,6 +108,28 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) reduce_stream_kernel(const 
                 stage = 0;
                 parity ^= 1u;
             }
+        }
+        if (S.inter_g > 0) {
+            // interleaved outputs: lane u of thread t carries output (t mod G) * V + u.  Warp butterfly over the lanes of
+            // equal class (xor masks >= G), one row of [warp][output] in shared memory, then thread o folds the 8 warps.
+            const int G = S.inter_g;
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                AT pu = stream_thread_lane_total<AT>(P, acc, u);
+                for (int m = 16; m >= G; m >>= 1) pu = red_apply<AT>(P.op, pu, shfl_xor_any(pu, m));
+                if (lane < G) fold[warp * STREAM_MAXOUT + lane * V + u] = pu;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+            if (tid < nout) {
+                AT q = fold[tid];
+#pragma unroll
+                for (int w = 1; w < THREADS / 32; ++w) q = red_apply<AT>(P.op, q, fold[w * STREAM_MAXOUT + tid]);
+                reinterpret_cast<AT *>(P.scratch)[(size_t)tid * grid + blockIdx.x] = q; // this CTA's partial of output tid
+            }
+            // (the partials were written by threads 0..nout-1; the barrier orders them before thread 0's acq_rel arrival
+            //  below, whose release is cumulative over everything that happens-before it)
+            asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+            break;
         }
         AT p = stream_thread_total<AT>(P, acc);
         if (blockIdx.x == 0 && tid == 0) p = stream_rest<AT, RC, NIN>(P, S, o, p);

@@ -167,7 +167,29 @@ def stream_reduction_cases(n=70001):
                                                                              ViewSpec(1, 0, (m1, m2, g), (1, m1, 2 * m1 * m2))], P_COPY, op=1, rtol=tol))
         A4 = ViewSpec(1, 0, (m1 * m2 // 2, 2, g), (1, m1 * m2 // 2, m1 * m2))  # kept dims 2 x g, runs of m1*m2/2
         out.append(Case(f"stream_2kept_{nm}", [np.zeros(2 * g, dt), a3], [ViewSpec(0, 0, (m1 * m2 // 2, 2, g), (0, g, 1)), A4], P_COPY, op=1, rtol=tol))
+        # kept dim INNERMOST and contiguous (column-major `mapreduce(f, op, A; dims=(2,3))`, BASELINE config 5 on one GPU):
+        # the interleaved mode of the streamed kernel, K * sizeof(T) = 16 ... 512 bytes, ragged reduced extent
+        esz = np.dtype(dt).itemsize
+        for K in sorted({16 // esz, 64 // esz, min(512 // esz, 64)}):
+            if K < 1:
+                continue
+            mm = (n * 8) // (K * esz) + 3
+            ai = (rand(rng, K * mm, dt) - 0.5).astype(dt)
+            AI = ViewSpec(1, 0, (K, mm), (1, K))
+            out.append(Case(f"stream_inter{K}_{nm}", [np.full(K, 2, dt), ai], [ViewSpec(0, 0, (K, mm), (1, 0)), AI], P_COPY, op=1, rtol=tol))
+            out.append(Case(f"stream_inter{K}_init0_rev_{nm}", [np.full(K, 2, dt), ai], [ViewSpec(0, K - 1, (K, mm), (-1, 0)), AI], P_COPY,
+                            op=1, initop=1, rtol=tol))
+        K = 64 // esz
+        mm = (n * 8) // (K * esz) + 1
+        ai, bi = (rand(rng, K * mm, dt) - 0.5).astype(dt), (rand(rng, K * mm, dt) - 0.5).astype(dt)
+        out.append(Case(f"stream_inter_dot_{nm}", [np.zeros(K, dt), ai, bi], [ViewSpec(0, 0, (K, mm), (1, 0)), ViewSpec(1, 0, (K, mm), (1, K)),
+                                                                                ViewSpec(2, 0, (K, mm), (1, K))], [A(0), A(1), F("mul")], op=1, rtol=tol))
+        # 3-D form as the adapters pass it: dims (K, m1, m2), reduced dims fuse (src/mapreduce.jl:98-117)
+        out.append(Case(f"stream_inter_3d_{nm}", [np.zeros(K, dt), ai], [ViewSpec(0, 0, (K, mm // 4, 4), (1, 0, 0)),
+                                                                           ViewSpec(1, 0, (K, mm // 4, 4), (1, K, K * (mm // 4)))], P_COPY, op=1, rtol=tol))
         if np.dtype(dt).kind == "f":
+            out.append(Case(f"stream_inter_max_{nm}", [np.full(K, -9, dt), ai], [ViewSpec(0, 0, (K, mm), (1, 0)), ViewSpec(1, 0, (K, mm), (1, K))],
+                            [A(0), F("abs")], op=4))
             out.append(Case(f"stream_abs2_{nm}", [np.zeros(1, dt), x], [O, X], [A(0), F("abs2")], op=1, rtol=tol))
             out.append(Case(f"stream_dims12_max_{nm}", [np.full(g, -9, dt), a3], [ViewSpec(0, 0, (m1, m2, g), (0, 0, 1)), A3], [A(0), F("abs")], op=4))
             out.append(Case(f"stream_max_{nm}", [np.full(1, -9, dt), x], [O, X], P_COPY, op=4))

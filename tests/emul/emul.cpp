@@ -256,13 +256,16 @@ template <class AT, int RC, int NIN> static void run_stream(const Plan &plan)
     std::vector<unsigned char> raw((size_t)S.stage_bytes + 64);
     unsigned char *stage = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(raw.data()) + 15) & ~(uintptr_t)15);
     std::vector<AT> partials((size_t)grid * (size_t)S.nout);
-    using Acc = AT[STREAM_ACC];
+    constexpr int V = StreamVec<AT>::V;
+    using Acc = AT[STREAM_ACC][V];
+    const int nruns = S.inter_g > 0 ? 1 : S.nout;
     for (int b = 0; b < grid; ++b) {
-        for (int o = 0; o < S.nout; ++o) {
+        for (int o = 0; o < nruns; ++o) {
             std::vector<char> accbuf(sizeof(Acc) * THREADS);
             Acc *acc = reinterpret_cast<Acc *>(accbuf.data());
             for (int t = 0; t < THREADS; ++t)
-                for (int q = 0; q < STREAM_ACC; ++q) acc[t][q] = red_neutral<AT>(P.op);
+                for (int q = 0; q < STREAM_ACC; ++q)
+                    for (int u = 0; u < V; ++u) acc[t][q][u] = red_neutral<AT>(P.op);
             for (int64_t c = b; c < S.nchunks; c += grid) {
                 const int64_t off = c * (int64_t)S.chunk_bytes;
                 const int64_t left = S.vec_bytes - off;
@@ -271,6 +274,27 @@ template <class AT, int RC, int NIN> static void run_stream(const Plan &plan)
                 for (int k = 0; k < S.nin; ++k)
                     std::memcpy(stage + (size_t)k * S.chunk_bytes, P.base[k + 1] + stream_out_offset(S, o, k) + off, (size_t)nb);
                 for (int t = 0; t < THREADS; ++t) stream_chunk<AT, RC, NIN>(P, S, stage, (int)(nb >> 4), t, acc[t]);
+            }
+            if (S.inter_g > 0) { // interleaved outputs: butterfly over lanes of equal class, [warp][output] rows, fold over warps
+                const int G = S.inter_g;
+                std::vector<AT> fold((size_t)(THREADS / 32) * STREAM_MAXOUT);
+                for (int w = 0; w < THREADS / 32; ++w)
+                    for (int u = 0; u < V; ++u) {
+                        AT p[32];
+                        for (int lane = 0; lane < 32; ++lane) p[lane] = stream_thread_lane_total<AT>(P, acc[w * 32 + lane], u);
+                        for (int m = 16; m >= G; m >>= 1) {
+                            AT q2[32];
+                            for (int lane = 0; lane < 32; ++lane) q2[lane] = red_apply<AT>(P.op, p[lane], p[lane ^ m]);
+                            std::memcpy(p, q2, sizeof q2);
+                        }
+                        for (int lane = 0; lane < G; ++lane) fold[(size_t)w * STREAM_MAXOUT + lane * V + u] = p[lane];
+                    }
+                for (int oo = 0; oo < S.nout; ++oo) {
+                    AT q = fold[(size_t)oo];
+                    for (int w = 1; w < THREADS / 32; ++w) q = red_apply<AT>(P.op, q, fold[(size_t)w * STREAM_MAXOUT + oo]);
+                    partials[(size_t)oo * grid + b] = q;
+                }
+                break;
             }
             AT wres[THREADS / 32];
             for (int w = 0; w < THREADS / 32; ++w) {
