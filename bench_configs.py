@@ -118,13 +118,25 @@ def run_all(eng, peak):
         out.append(_entry(f"C3 f64 {m}^4 permutedims (4,3,2,1) (rot)", 2 * m ** 4 * 8, ms, peak, sets=k, kernel=_kernel([], 0, 0, shape, list(pairs[0]))))
         ms = _time(lambda i: sb.copy_(*pairs[0]), 300)
         out.append(_entry(f"C3 f64 {m}^4 permutedims (4,3,2,1) (warm, L2-resident)", 2 * m ** 4 * 8, ms, peak))
-        # eight independent problems of this size as ONE batch (sb_mapreduce_batch): the calls overlap on side streams /
-        # parallel graph branches instead of queueing behind each other's launch + DRAM latency; time PER PROBLEM
-        nb = 8
-        batches = [[([], 0, 0, 0.0, shape, list(pairs[(j * nb + q) % k])) for q in range(nb)] for j in range(max(1, k // nb))]
-        ms = _time(lambda i: sb.run_batch(batches[i % len(batches)]), 10 * len(batches)) / nb
-        out.append(_entry(f"C3 f64 {m}^4 permutedims (4,3,2,1) x{nb} in one batch (rot, per problem)", 2 * m ** 4 * 8, ms, peak, batch=nb,
-                          kernel="sb_mapreduce_batch: " + _kernel([], 0, 0, shape, list(pairs[0]))))
+        # independent problems of this size as ONE batch (sb_mapreduce_batch): calls that share a plan are merged into one
+        # grouped launch (tma_kernel.cuh "GROUP"), so the tiles of all problems stream through one persistent grid instead of
+        # paying one launch + one DRAM round trip per statement; time PER PROBLEM
+        for nb in (8, 16):
+            batches = [[([], 0, 0, 0.0, shape, list(pairs[(j * nb + q) % k])) for q in range(nb)] for j in range(max(1, k // nb))]
+            eng.reset_stats()
+            sb.run_batch(batches[0])
+            st = eng.stats()
+            ms = _time(lambda i: sb.run_batch(batches[i % len(batches)]), 10 * len(batches)) / nb
+            out.append(_entry(f"C3 f64 {m}^4 permutedims (4,3,2,1) x{nb} in one batch (rot, per problem)", 2 * m ** 4 * 8, ms, peak, batch=nb,
+                              launches_per_batch=st["launches"], grouped_calls=st["grouped_calls"],
+                              kernel=f"sb_mapreduce_batch, {st['launches']} grouped launch(es) for {nb} calls: " + _kernel([], 0, 0, shape, list(pairs[0]))))
+        # the size-matched yardstick: a dense copy of the same 16.8 MB through the engine (what launch + ramp + drain cost
+        # at this size, whatever the access pattern)
+        dense = [(sb.StridedView(Bs[i]), sb.StridedView(As[i])) for i in range(k)]
+        ms = _time(lambda i: sb.copy_(*dense[i % k]), 20 * k)
+        out.append(_entry(f"dense copy f64 {m}^4 elements (rot; size-matched yardstick for C3 / C4')", 2 * m ** 4 * 8, ms, peak, sets=k,
+                          kernel=_kernel([], 0, 0, dense[0][0].size, list(dense[0]))))
+        del dense
         del As, Bs, pairs, batches
 
     # C4: F32 64^4 and C4': F64 32^4 4-way permutedims sum

@@ -145,6 +145,10 @@ int sb_ctx_reload_env(sb_ctx *ctx);
 int sb_sync(sb_ctx *ctx);
 const char *sb_last_error(sb_ctx *ctx); /* ctx may be NULL: last error of the calling thread        */
 int sb_abi_version(void);
+/* Waits for the background NVRTC compiles of this process (jit.cu).  Call it from the host's exit hook (Python `atexit`,
+ * Julia `atexit`): a process must not run its exit handlers while a worker thread is still inside NVRTC.  Contexts stay
+ * valid; idempotent; the library also registers it with atexit itself as a second line of defence. */
+int sb_shutdown(void);
 
 /* ---- device memory helpers for hosts without their own CUDA allocator (the Julia glue) ---------- */
 int sb_malloc(sb_ctx *ctx, size_t bytes, void **out);
@@ -160,7 +164,10 @@ int sb_mapreduce(sb_ctx *ctx, const sb_desc *desc);
 /* n calls as ONE batch (device pointers).  Small problems are bound by launch and DRAM latency (~4 us each on a B200,
  * whatever the kernel does); the batch runs its INDEPENDENT map calls -- output byte range disjoint from every other
  * call's operands -- concurrently on side streams between a fork and a join on the ctx's stream, everything else
- * (reductions, chains such as B = f(A); C = g(B)) in order after the join.  Results are the same as n sb_mapreduce calls
+ * (reductions, chains such as B = f(A); C = g(B)) in order after the join.  Independent calls that share ONE plan (same
+ * dims, strides, eltypes and program; only the base pointers differ) and take the TMA ring kernel are merged into a single
+ * grouped launch of up to 16 problems (`sb_stats.grouped_calls`): a block of equal-shape `permutedims!` then streams at
+ * HBM speed instead of paying one launch + one DRAM round trip per statement.  Results are the same as n sb_mapreduce calls
  * in order.  Capturable in a CUDA graph (parallel branches) once a batch has run outside the capture.  The reference
  * issues one `_mapreduce_fuse!` per statement (src/mapreduce.jl:98); this is the entry a glue uses for a block of
  * independent `@strided` statements. */
@@ -224,6 +231,7 @@ typedef struct sb_stats {
     uint64_t jit_launches; /* launches of NVRTC-specialised kernels (subset of `launches`) */
     uint64_t zero_copy_calls; /* sb_mapreduce_host calls served without staging (kernel reads/writes pinned host memory) */
     uint64_t batches;         /* sb_mapreduce_batch calls */
+    uint64_t grouped_calls;   /* calls of a batch that shared ONE launch with other calls of the same plan */
 } sb_stats;
 int sb_get_stats(sb_ctx *ctx, sb_stats *out);
 int sb_reset_stats(sb_ctx *ctx);

@@ -44,6 +44,8 @@ function ctx()
     if CTX[] == C_NULL
         rc = ccall((:sb_ctx_create, LIB), Cint, (Cint, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), 0, C_NULL, CTX)
         rc == 0 || error("sb_ctx_create failed ($rc): no B200 available")
+        # background NVRTC compiles must have finished before the process runs its exit handlers (include/strided_b200.h)
+        atexit(() -> ccall((:sb_shutdown, LIB), Cint, ()))
     end
     return CTX[]
 end

@@ -54,7 +54,7 @@ class sb_desc(C.Structure):
 class sb_stats(C.Structure):
     _fields_ = [("launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("plans_built", C.c_uint64), ("plans_cached", C.c_uint64), ("jit_launches", C.c_uint64),
-                ("zero_copy_calls", C.c_uint64), ("batches", C.c_uint64)]
+                ("zero_copy_calls", C.c_uint64), ("batches", C.c_uint64), ("grouped_calls", C.c_uint64)]
 
 
 class StridedB200Error(RuntimeError):
@@ -79,7 +79,7 @@ EXPORTS = [
     "sb_abi_version", "sb_ctx_create", "sb_ctx_destroy", "sb_ctx_set_stream", "sb_ctx_set_sync", "sb_ctx_reload_env", "sb_sync",
     "sb_last_error", "sb_malloc", "sb_free", "sb_memcpy_h2d", "sb_memcpy_d2h", "sb_mapreduce", "sb_mapreduce_batch",
     "sb_mapreduce_host", "sb_plan_describe", "sb_get_stats", "sb_reset_stats",
-    "sb_peer_export", "sb_peer_attach", "sb_peer_detach", "sb_mapreduce_allreduce",
+    "sb_peer_export", "sb_peer_attach", "sb_peer_detach", "sb_mapreduce_allreduce", "sb_shutdown",
 ]
 SB_PEER_MAX_OUT, SB_PEER_MAX_WORLD, SB_IPC_HANDLE_BYTES = 1024, 8, 64
 
@@ -126,6 +126,10 @@ def load_library():
     for n in EXPORTS:
         if n != "sb_last_error":
             getattr(lib, n).restype = i32
+    lib.sb_shutdown.argtypes = []
+    # the interpreter must not run its exit handlers while a background NVRTC compile is still in flight (jit.cu)
+    import atexit
+    atexit.register(lib.sb_shutdown)
     _lib = lib
     return lib
 

@@ -68,6 +68,7 @@ void env_reload()
     const char *e = std::getenv("SB_JIT_MIN_ELEMENTS");
     c.jit_min_elements = e ? std::atoll(e) : (1ll << 18);
     c.jit_sync = std::getenv("SB_JIT_SYNC") != nullptr;
+    c.no_group = std::getenv("SB_NO_GROUP") != nullptr;
 }
 cudaError_t ensure_dynamic_smem(const void *func, size_t smem)
 {
@@ -249,6 +250,12 @@ static int peer_check(sb_ctx *ctx)
 extern "C" {
 
 int sb_abi_version(void) { return SB_ABI_VERSION; }
+
+int sb_shutdown(void)
+{
+    sb::jit_join_workers();
+    return SB_OK;
+}
 
 const char *sb_last_error(sb_ctx *ctx)
 {
@@ -772,6 +779,54 @@ static void desc_ranges(const sb_desc &d, uintptr_t (&lo)[SB_MAX_OPS], uintptr_t
     }
 }
 
+// Several problems of ONE cached plan (same dims, strides, eltypes, program, alias pattern; different base pointers) that
+// take the TMA ring kernel: one grouped launch (tma_kernel.cuh "GROUP") instead of one launch each.  Returns false when
+// the plan or a problem does not qualify at bind time (the caller then issues the calls one by one).
+static bool group_plan_ok(sb_ctx *ctx, const CachedPlan &cp)
+{
+    const Plan &pl = cp.plan;
+    if (pl.kind != PLAN_MAP || !pl.tma_ok || pl.needs_jit || pl.tma.nin > TMA_GROUP_MAXIN) return false;
+    if (pl.orbit_ok && cp.dev_orbit) return false;
+    if (pl.key.recipe == RC_INTERP && jit_enabled() && pl.elements >= (int64_t)env_cache().jit_min_elements) return false; // NVRTC-specialised kernel
+    if (env_cache().no_group) return false;
+    (void)ctx;
+    return find_tma_group_kernel(pl.key) != nullptr;
+}
+
+static int run_group(sb_ctx *ctx, const sb_desc *descs, const int *idx, int cnt, const CachedPlan &cp, bool *done)
+{
+    *done = false;
+    Plan plan = cp.plan;
+    plan.map.tile_order = (const int32_t *)cp.dev_order;
+    plan.map.tile_desc = (const TileDesc *)cp.dev_desc;
+    const TmaGroupEntry *gk = find_tma_group_kernel(plan.key);
+    if (!gk) return SB_OK;
+    TmaGroup G;
+    std::memset(&G, 0, sizeof G);
+    G.nprob = cnt;
+    for (int p = 0; p < cnt; ++p) {
+        const sb_desc &d = descs[idx[p]];
+        if (plan.map.shift_last && output_overlaps_inputs(d)) return SB_OK; // in-place update: masked edge tiles, LSU kernel
+        for (int k = 0; k < MAXO; ++k) plan.map.base[k] = (unsigned char *)d.base[plan.base_src[k] < d.nops ? plan.base_src[k] : 0];
+        alignas(64) CUtensorMap maps[TMA_MAXIN];
+        if (!encode_tma_maps(plan, maps)) return SB_OK;
+        for (int k = 0; k < TMA_GROUP_MAXIN; ++k) G.maps[p][k] = maps[k < plan.tma.nin ? k : 0];
+        G.out[p] = plan.map.base[0];
+    }
+    cudaSetDevice(ctx->device);
+    int nb = 1;
+    int rc = occupancy_of(ctx, gk->func, gk->occupancy, (size_t)plan.tma_smem_bytes, nb);
+    if (rc != SB_OK) return rc;
+    int64_t grid = std::min<int64_t>(plan.map.ntiles * cnt, (int64_t)ctx->dev.sm_count * nb);
+    if (grid < 1) grid = 1;
+    cudaError_t e = gk->launch(plan.map, plan.tma, G, (int)grid, (size_t)plan.tma_smem_bytes, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "map_tma_group launch");
+    ctx->stats.launches++;
+    ctx->stats.grouped_calls += (uint64_t)cnt;
+    *done = true;
+    return SB_OK;
+}
+
 extern "C" int sb_mapreduce_batch(sb_ctx *ctx, int n, const sb_desc *descs)
 {
     if (!ctx) return set_err(nullptr, SB_E_INVALID, "sb_mapreduce_batch: null ctx");
@@ -817,8 +872,52 @@ extern "C" int sb_mapreduce_batch(sb_ctx *ctx, int n, const sb_desc *descs)
             parallel[i] = indep ? 1 : 0;
         }
     }
-    int npar = 0;
-    for (int i = 0; i < n; ++i) npar += parallel[i];
+    // units of independent work: a single call, or a group of calls that share one plan (one launch, see run_group)
+    struct Unit {
+        std::vector<int> idx;
+        const CachedPlan *cp = nullptr; // != nullptr: grouped launch
+    };
+    std::vector<Unit> units;
+    {
+        std::vector<const CachedPlan *> cps((size_t)n, nullptr);
+        if (ctx->plans.size() < 4000) // (lookup_plan drops the whole cache beyond 4096 entries: no pointers across that)
+            for (int i = 0; i < n; ++i) {
+                if (!parallel[i]) continue;
+                PlanIt hit;
+                const int rc = lookup_plan(ctx, descs[i], false, hit);
+                if (rc != SB_OK) return rc;
+                if (group_plan_ok(ctx, hit->second)) cps[i] = &hit->second;
+            }
+        std::vector<char> taken((size_t)n, 0);
+        for (int i = 0; i < n; ++i) {
+            if (!parallel[i] || taken[i]) continue;
+            Unit u;
+            u.idx.push_back(i);
+            taken[i] = 1;
+            if (cps[i]) {
+                for (int j = i + 1; j < n && (int)u.idx.size() < TMA_GROUP_MAX; ++j)
+                    if (parallel[j] && !taken[j] && cps[j] == cps[i]) {
+                        u.idx.push_back(j);
+                        taken[j] = 1;
+                    }
+                if (u.idx.size() >= 2) u.cp = cps[i];
+            }
+            units.push_back(std::move(u));
+        }
+    }
+    auto run_unit = [&](const Unit &u) -> int {
+        if (u.cp) {
+            bool done = false;
+            const int rc = run_group(ctx, descs, u.idx.data(), (int)u.idx.size(), *u.cp, &done);
+            if (rc != SB_OK || done) return rc;
+        }
+        for (int i : u.idx) {
+            const int rc = run_desc(ctx, descs[i]);
+            if (rc != SB_OK) return rc;
+        }
+        return SB_OK;
+    };
+    const int npar = (int)units.size();
     cudaStream_t main_stream = ctx->stream;
     int used = 0;
     if (npar >= 2) {
@@ -839,11 +938,10 @@ extern "C" int sb_mapreduce_batch(sb_ctx *ctx, int n, const sb_desc *descs)
         for (int q = 0; q < used && e == cudaSuccess; ++q) e = cudaStreamWaitEvent(ctx->side[q], ctx->ev_fork, 0);
         if (e != cudaSuccess) return cuda_fail(ctx, e, "batch fork");
         int slot = 0, rc = SB_OK;
-        for (int i = 0; i < n && rc == SB_OK; ++i) {
-            if (!parallel[i]) continue;
+        for (size_t q = 0; q < units.size() && rc == SB_OK; ++q) {
             ctx->stream = ctx->side[slot % used];
             ++slot;
-            rc = run_desc(ctx, descs[i]);
+            rc = run_unit(units[q]);
         }
         ctx->stream = main_stream;
         for (int q = 0; q < used; ++q) { // always join, also on error: the side streams must not stay forked (capture!)
@@ -852,9 +950,13 @@ extern "C" int sb_mapreduce_batch(sb_ctx *ctx, int n, const sb_desc *descs)
             if (e2 != cudaSuccess && rc == SB_OK) rc = cuda_fail(ctx, e2, "batch join");
         }
         if (rc != SB_OK) return rc;
+    } else if (npar == 1 && units[0].cp) { // one group and nothing else to overlap with: on the ctx's stream, in order
+        const int rc = run_unit(units[0]);
+        if (rc != SB_OK) return rc;
+        for (int i : units[0].idx) parallel[i] = 2; // done
     }
     for (int i = 0; i < n; ++i) {
-        if (npar >= 2 && parallel[i]) continue;
+        if ((npar >= 2 && parallel[i]) || parallel[i] == 2) continue;
         const int rc = run_desc(ctx, descs[i]);
         if (rc != SB_OK) return rc;
     }

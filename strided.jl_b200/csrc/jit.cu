@@ -244,12 +244,25 @@ struct Job {
 };
 std::map<std::string, Job> g_jobs;
 std::vector<std::thread> g_workers;
-struct WorkerJoin {
-    ~WorkerJoin()
+std::mutex g_workers_mu;
+
+// Waits for the compiles that are still running on worker threads.  A process that exits while NVRTC is compiling would
+// tear libnvrtc's own static state down under the worker (libnvrtc is dlopen'ed AFTER this library, so its destructors run
+// BEFORE ours): the handler is therefore registered with atexit at every spawn -- later than anything NVRTC has registered
+// up to then -- and hosts call it explicitly through sb_shutdown (Python: atexit hook in abi.py; Julia: atexit in the glue).
+void jit_join_workers()
+{
+    std::vector<std::thread> ws;
     {
-        for (auto &t : g_workers)
-            if (t.joinable()) t.join();
+        std::lock_guard<std::mutex> lk(g_workers_mu);
+        ws.swap(g_workers);
     }
+    for (auto &t : ws)
+        if (t.joinable()) t.join();
+}
+
+struct WorkerJoin {
+    ~WorkerJoin() { jit_join_workers(); }
 } g_worker_join;
 
 // everything that does not need a CUDA context: source generation, disk cache, NVRTC
@@ -347,7 +360,11 @@ const JitKernel *jit_get(int kind, const KernelKey &key, const Program &prog, bo
             compile_job(skey, kind, key, prog);
             lk.lock();
         } else {
-            g_workers.emplace_back(compile_job, skey, kind, key, prog);
+            {
+                std::lock_guard<std::mutex> wl(g_workers_mu);
+                g_workers.emplace_back(compile_job, skey, kind, key, prog);
+            }
+            std::atexit(jit_join_workers);
             return nullptr; // the interpreter serves this call
         }
         it = g_jobs.find(skey);

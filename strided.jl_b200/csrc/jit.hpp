@@ -25,5 +25,6 @@ enum JitKind : int { JIT_MAP = 0, JIT_REDUCE = 1 };
 const JitKernel *jit_get(int kind, const KernelKey &key, const Program &prog, bool wait);
 const char *jit_last_log();
 bool jit_enabled();
+void jit_join_workers(); // waits for background compiles (atexit / sb_shutdown)
 
 } // namespace sb

@@ -15,6 +15,7 @@ struct EnvCache {
     bool fused_peer = true;                // SB_NO_FUSED_PEER
     long long jit_min_elements = 1 << 18;  // SB_JIT_MIN_ELEMENTS
     bool jit_sync = false;                 // SB_JIT_SYNC: block on the NVRTC compile instead of compiling in the background
+    bool no_group = false;                 // SB_NO_GROUP: sb_mapreduce_batch never merges same-plan calls into one launch
 };
 EnvCache &env_cache();  // abi.cu
 void env_reload();      // abi.cu

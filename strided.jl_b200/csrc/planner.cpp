@@ -1078,6 +1078,10 @@ bool orbit_items(const Canon &c, const OrbitGeom &G, const DeviceInfo &dev, std:
     {
         int f = 1;
         while (f < 4 && f * 2 <= gmax && (int64_t)items.size() * f * 2 <= (int64_t)dev.sm_count) f *= 2;
+        if (const char *e = std::getenv("SB_ORBIT_SPLIT")) { // tuning knob (tools/): force the split factor
+            const int v = std::atoi(e);
+            if ((v == 1 || v == 2 || v == 4) && v <= gmax) f = v;
+        }
         if (f > 1) {
             std::vector<OrbitItem> split;
             for (const OrbitItem &it : items) {

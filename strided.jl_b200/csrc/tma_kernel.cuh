@@ -118,10 +118,22 @@ constexpr int TMA_THREADS = THREADS + 32;
 //   consumer warps: wait on the full barrier, read the tile from shared memory in OUTPUT order, evaluate f, store,
 //                   then release the stage (one arrive per warp on the empty barrier).
 // No CTA-wide barrier in the loop: the producer runs up to `nstage` tiles ahead of the slowest consumer warp.
-template <class CT, int RC, int NIN, int EPT>
-__global__ void __launch_bounds__(TMA_THREADS, SB_TMA_MINB)
-map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaParams T, const __grid_constant__ CUtensorMap m0,
-               const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2, const __grid_constant__ CUtensorMap m3)
+//
+// GROUP: several problems of ONE plan (same dims, strides, eltypes and program; different base pointers) in one launch --
+// sb_mapreduce_batch's answer to launch- and latency-bound sizes (1000^2, 32^4: one wave of tiles each).  Global position
+// g = problem * ntiles + tile; the problem selects the tensor maps and the output base, everything else is the plan's.
+constexpr int TMA_GROUP_MAX = 16; // problems per launch
+constexpr int TMA_GROUP_MAXIN = 2;
+struct TmaGroup {
+    int32_t nprob;
+    int32_t pad_[15];
+    unsigned char *out[TMA_GROUP_MAX];                              // output base of problem p (view offset included)
+    alignas(64) CUtensorMap maps[TMA_GROUP_MAX][TMA_GROUP_MAXIN];   // tensor maps of problem p's inputs
+};
+
+template <class CT, int RC, int NIN, int EPT, bool GROUP>
+__device__ __forceinline__ void map_tma_body(const MapParams &P, const TmaParams &T, const CUtensorMap *m0, const CUtensorMap *m1,
+                                             const CUtensorMap *m2, const CUtensorMap *m3, const TmaGroup *G)
 {
     extern __shared__ unsigned char sb_tma_smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[TMA_MAXSTAGE];
@@ -140,7 +152,8 @@ map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaP
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const uint32_t ntiles = (uint32_t)P.ntiles;
+    const uint32_t ntiles1 = (uint32_t)P.ntiles;                                   // tiles of one problem
+    const uint32_t ntiles = GROUP ? ntiles1 * (uint32_t)G->nprob : ntiles1;        // positions of this launch
     const uint32_t grid = gridDim.x;
     if (warp == THREADS / 32) {
         // ---------------- producer warp ----------------
@@ -154,7 +167,7 @@ map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaP
                         bq = q;
                     }
         }
-        const CUtensorMap *map = bk == 0 ? &m0 : bk == 1 ? &m1 : bk == 2 ? &m2 : &m3;
+        const CUtensorMap *map = bk == 0 ? m0 : bk == 1 ? m1 : bk == 2 ? m2 : m3;
         const uint32_t box_dst = bk >= 0 ? (uint32_t)T.op[bk].smem_off + (uint32_t)(bq * T.op[bk].box_bytes) : 0u;
         int my_cdim[TMA_MAXRANK] = {0, 0, 0, 0, 0};
         int my_rank = 1, my_inner_step = 0;
@@ -176,9 +189,15 @@ map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaP
         // sooner and costs config 2 10 % (47.6 vs 42.7 us, profiles/r02_tma_prefetch_bisect.txt) -- the alias-aware tile
         // order relies on the A and A' tiles of neighbouring CTAs meeting in L2, and that pacing is part of it.
         TileDesc td_first = {};
-        if (P.tile_desc && blockIdx.x < ntiles) td_first = P.tile_desc[blockIdx.x];
+        if (P.tile_desc && blockIdx.x < ntiles) td_first = P.tile_desc[GROUP ? blockIdx.x % ntiles1 : blockIdx.x];
         pdl_wait(); // the operands may be the previous kernel's output
-        for (uint32_t pos = blockIdx.x; pos < ntiles; pos += grid) {
+        for (uint32_t gpos = blockIdx.x; gpos < ntiles; gpos += grid) {
+            uint32_t pos = gpos;
+            if (GROUP) {
+                const uint32_t prob = gpos / ntiles1;
+                pos = gpos - prob * ntiles1;
+                if (bk >= 0) map = &G->maps[prob][bk < TMA_GROUP_MAXIN ? bk : 0];
+            }
             mbar_wait(smem_u32(&empty_bar[stage]), parity);
             const uint32_t fb = smem_u32(&full_bar[stage]);
             if (lane == 0) mbar_expect_tx(fb, (uint32_t)T.stage_bytes);
@@ -189,7 +208,7 @@ map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaP
                 const uint32_t dst = ring_u32 + (uint32_t)(stage * T.stage_bytes) + box_dst;
                 if (P.tile_desc) { // precomputed tile record: coordinates are a per-lane permutation of the origins
                     TileDesc td = td_first;
-                    if (pos != blockIdx.x) td = P.tile_desc[pos];
+                    if (gpos != blockIdx.x) td = P.tile_desc[pos];
                     int32_t crd[TMA_MAXRANK];
 #pragma unroll
                     for (int i = 0; i < TMA_MAXRANK; ++i) {
@@ -224,18 +243,26 @@ map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaP
         int stage = 0;
         uint32_t parity = 0;
         TileDesc td_first = {}; // (first record fetched before the wait, see the producer)
-        if (P.tile_desc && blockIdx.x < ntiles) td_first = P.tile_desc[blockIdx.x];
+        if (P.tile_desc && blockIdx.x < ntiles) td_first = P.tile_desc[GROUP ? blockIdx.x % ntiles1 : blockIdx.x];
         pdl_wait(); // the output may still be read or written by the previous kernel
-        for (uint32_t pos = blockIdx.x; pos < ntiles; pos += grid) {
+        for (uint32_t gpos = blockIdx.x; gpos < ntiles; gpos += grid) {
+            uint32_t pos = gpos;
+            unsigned char *obase = P.base[0];
+            if (GROUP) {
+                const uint32_t prob = gpos / ntiles1;
+                pos = gpos - prob * ntiles1;
+                obase = G->out[prob];
+            }
             MapTile<1> tl;
             if (P.tile_desc) {
                 TileDesc td = td_first;
-                if (pos != blockIdx.x) td = P.tile_desc[pos];
+                if (gpos != blockIdx.x) td = P.tile_desc[pos];
                 tl.id = td.id_full & 0x7fffffffu;
                 tl.full = (td.id_full >> 31) != 0;
-                tl.ptr[0] = P.base[0] + (td.out_off + th0.g_toff[0]);
+                tl.ptr[0] = obase + (td.out_off + th0.g_toff[0]);
             } else {
                 map_tile_init<1>(P, th0, pos, tl);
+                if (GROUP) tl.ptr[0] = obase + (tl.ptr[0] - P.base[0]);
             }
             mbar_wait(smem_u32(&full_bar[stage]), parity);
             tma_consume<CT, RC, NIN, EPT>(P, T, th, th0, tl, t, ring + (size_t)stage * T.stage_bytes);
@@ -247,6 +274,22 @@ map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaP
             }
         }
     }
+}
+
+template <class CT, int RC, int NIN, int EPT>
+__global__ void __launch_bounds__(TMA_THREADS, SB_TMA_MINB)
+map_tma_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaParams T, const __grid_constant__ CUtensorMap m0,
+               const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2, const __grid_constant__ CUtensorMap m3)
+{
+    map_tma_body<CT, RC, NIN, EPT, false>(P, T, &m0, &m1, &m2, &m3, nullptr);
+}
+
+template <class CT, int RC, int NIN, int EPT>
+__global__ void __launch_bounds__(TMA_THREADS, SB_TMA_MINB)
+map_tma_group_kernel(const __grid_constant__ MapParams P, const __grid_constant__ TmaParams T, const __grid_constant__ TmaGroup G)
+{
+    static_assert(NIN <= TMA_GROUP_MAXIN, "grouped launches carry two tensor maps per problem");
+    map_tma_body<CT, RC, NIN, EPT, true>(P, T, nullptr, nullptr, nullptr, nullptr, &G);
 }
 
 struct TmaEntry {
@@ -280,5 +323,37 @@ template <class CT, int RC, int NIN, int EPT> struct TmaLaunch {
 
 const TmaEntry *tma_table(int *n);
 const TmaEntry *find_tma_kernel(const KernelKey &k);
+
+// grouped launches (kernels_tma_group.cu): the same kernels for <= TMA_GROUP_MAXIN inputs
+struct TmaGroupEntry {
+    KernelKey key;
+    cudaError_t (*launch)(const MapParams &, const TmaParams &, const TmaGroup &, int grid, size_t smem, cudaStream_t);
+    cudaError_t (*occupancy)(int *nblocks, size_t smem);
+    const void *func;
+};
+
+template <class CT, int RC, int NIN, int EPT> struct TmaGroupLaunch {
+    static cudaError_t launch(const MapParams &P, const TmaParams &T, const TmaGroup &G, int grid, size_t smem, cudaStream_t s)
+    {
+        auto k = map_tma_group_kernel<CT, RC, NIN, EPT>;
+        cudaError_t e = ensure_dynamic_smem((const void *)k, smem);
+        if (e != cudaSuccess) return e;
+        return launch_pdl(k, grid, TMA_THREADS, smem, s, P, T, G);
+    }
+    static cudaError_t occupancy(int *nb, size_t smem)
+    {
+        auto k = map_tma_group_kernel<CT, RC, NIN, EPT>;
+        cudaError_t e = ensure_dynamic_smem((const void *)k, smem);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, TMA_THREADS, smem);
+    }
+    static const void *func() { return (const void *)map_tma_group_kernel<CT, RC, NIN, EPT>; }
+};
+
+#define SB_TMA_GROUP_ENTRY(CT, DT, RC, NIN, EPT)                                                                     \
+    TmaGroupEntry { KernelKey{DT, RC, NIN, EPT, 1}, &TmaGroupLaunch<CT, RC, NIN, EPT>::launch,                       \
+                    &TmaGroupLaunch<CT, RC, NIN, EPT>::occupancy, TmaGroupLaunch<CT, RC, NIN, EPT>::func() }
+
+const TmaGroupEntry *find_tma_group_kernel(const KernelKey &k);
 
 } // namespace sb

@@ -88,3 +88,96 @@ def test_batch_in_cuda_graph():
             assert torch.equal(got, want)
     finally:
         eng.set_sync(True)
+
+
+def _same_plan_calls(dev, nprob, seed=11):
+    """nprob independent problems of ONE plan: `permutedims!(B_i, A_i, (4,3,2,1))` at 32^4 (BASELINE config 3) -- and the
+    torch results they must equal bit for bit."""
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    sh = (32, 32, 32, 32)
+    calls, checks = [], []
+    for _ in range(nprob):
+        a = torch.randn(32 ** 4, dtype=torch.float64, device=dev, generator=g)
+        b = torch.zeros_like(a)
+        calls.append((P_COPY, 0, 0, 0.0, sh, [sb.StridedView(b, sh, _col(sh)), sb.StridedView(a, sh, _col(sh)).permutedims((3, 2, 1, 0))]))
+        checks.append((b, a.view(*sh).permute(3, 2, 1, 0).contiguous().view(-1)))
+    return calls, checks
+
+
+@pytest.mark.parametrize("nprob", [2, 8, 19])
+def test_same_plan_calls_share_one_launch(nprob):
+    # equal-shape statements are merged into grouped launches of up to 16 problems (tma_kernel.cuh "GROUP")
+    import torch
+    dev = torch.device("cuda", 0)
+    eng = sb.get_engine(0)
+    calls, checks = _same_plan_calls(dev, nprob)
+    assert calls[0][5][0].parent.numel() == 32 ** 4
+    eng.reset_stats()
+    sb.run_batch(calls)
+    torch.cuda.synchronize()
+    st = eng.stats()
+    assert st["grouped_calls"] == nprob and st["launches"] == (nprob + 15) // 16
+    for got, want in checks:
+        assert torch.equal(got, want)
+
+
+def test_grouped_two_input_map_and_graph_replay():
+    # (A_i .+ B_i') ./ 2 at 512^2, eight problems in one launch; replayed from a CUDA graph with fresh data
+    import torch
+    dev = torch.device("cuda", 0)
+    eng = sb.get_engine(0)
+    n, nprob = 512, 8
+    g = torch.Generator(device=dev)
+    g.manual_seed(23)
+    prog = [A(0), A(1), F("add"), K(2), F("div")]
+    As = [torch.randn(n * n, dtype=torch.float64, device=dev, generator=g) for _ in range(nprob)]
+    Bs = [torch.randn(n * n, dtype=torch.float64, device=dev, generator=g) for _ in range(nprob)]
+    Os = [torch.zeros(n * n, dtype=torch.float64, device=dev) for _ in range(nprob)]
+    calls = [(prog, 0, 0, 0.0, (n, n), [sb.StridedView(o, (n, n), (1, n)), sb.StridedView(a, (n, n), (1, n)), sb.StridedView(b, (n, n), (1, n)).T])
+             for o, a, b in zip(Os, As, Bs)]
+
+    def want(i):  # column-major flat of (A + B') / 2  ==  row-major flat of its transpose
+        return ((As[i].view(n, n) + Bs[i].view(n, n).t()) / 2).contiguous().view(-1)
+
+    eng.reset_stats()
+    sb.run_batch(calls)
+    torch.cuda.synchronize()
+    assert eng.stats()["grouped_calls"] == nprob and eng.stats()["launches"] == 1
+    for i in range(nprob):
+        assert torch.equal(Os[i], want(i))
+    eng.set_sync(False)
+    side = torch.cuda.Stream()
+    try:
+        with torch.cuda.stream(side):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=side):
+                sb.run_batch(calls)
+            for a in As:
+                a.normal_(generator=g)
+            for o in Os:
+                o.zero_()
+            gr.replay()
+            torch.cuda.synchronize()
+        for i in range(nprob):
+            assert torch.equal(Os[i], want(i))
+    finally:
+        eng.set_sync(True)
+
+
+def test_grouping_respects_dependencies_and_inplace():
+    # B = permute(A); C = permute(B): same plan, but the second reads what the first writes -> not grouped, in order
+    import torch
+    dev = torch.device("cuda", 0)
+    eng = sb.get_engine(0)
+    sh = (32, 32, 32, 32)
+    a = torch.randn(32 ** 4, dtype=torch.float64, device=dev)
+    b, c = torch.zeros_like(a), torch.zeros_like(a)
+    V = lambda t: sb.StridedView(t, sh, _col(sh))
+    calls = [(P_COPY, 0, 0, 0.0, sh, [V(b), V(a).permutedims((3, 2, 1, 0))]), (P_COPY, 0, 0, 0.0, sh, [V(c), V(b).permutedims((3, 2, 1, 0))])]
+    eng.reset_stats()
+    sb.run_batch(calls)
+    torch.cuda.synchronize()
+    assert eng.stats()["grouped_calls"] == 0 and eng.stats()["launches"] == 2
+    assert torch.equal(c, a)  # the reversal is an involution (benchmarks/benchtests.jl:40)
