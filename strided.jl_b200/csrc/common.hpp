@@ -175,7 +175,14 @@ struct MapParams {
     // overlaps no input (decided at bind time; in-place updates keep the masked edge tiles).
     int32_t excess[MAXD]; // 0: dim is tiled exactly or is shorter than one tile
     int32_t shift_last;
-    int32_t pad_shift_;
+    // Balanced tiles (umask = 1): the thread map stays a power-of-two box of 2^cbits per tile dim, but only the first
+    // tile_b[d] <= 2^cbits coordinates of it are used -- tile_b[d] = ceil(dims / ceil(dims / 2^cbits)) -- so that
+    // ceil(dims/2^cbits) tiles cover the dim with (almost) no overlap: 70 = 3 x 24 instead of 3 x 32 with 26 elements
+    // computed twice.  Every tile then has the SAME valid region: its packed mask `urg` is a plan constant, no per-tile
+    // decode.  Idle lanes cost issue slots, not memory requests (reversal permute of 70^4: L2<->SM traffic 1.88x -> 1.06x).
+    int32_t umask;
+    uint32_t urg;    // packed (tile_b - 1 | guard) of a balanced tile (see pack_rem)
+    int32_t pad_um_;
     FastDiv tdiv[MAXD];   // division by ntile[d]
     int64_t tstep[MAXO][MAXD]; // BYTES per tile step along d: tile_b[d] * strides[k][d] * sizeof(elem k)
     uint8_t tdim[MAXTD];  // tile-dim slot -> canonical dim

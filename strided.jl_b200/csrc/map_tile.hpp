@@ -100,8 +100,9 @@ SB_HD uint32_t map_tile_rem(const MapParams &P, uint32_t id)
     }
     int32_t rem[MAXTD];
     for (int i = 0; i < P.ntd; ++i) {
-        const int64_t r = P.dims[P.tdim[i]] - origin[P.tdim[i]];
-        rem[i] = r > 0x7fffffff ? 0x7fffffff : (int32_t)r;
+        int64_t r = P.dims[P.tdim[i]] - origin[P.tdim[i]];
+        if (r > P.tile_b[P.tdim[i]]) r = P.tile_b[P.tdim[i]]; // (balanced tiles use fewer coordinates than the box holds)
+        rem[i] = (int32_t)r;
     }
     return pack_rem(rem, P.ntd, P.cpos, P.cbits, P.guard);
 }
@@ -136,7 +137,7 @@ SB_HD void map_phase1(const MapParams &P, const MapThread<NIN + 1> &th, const Ma
     constexpr int V = VecOf<CT>::V;
     constexpr bool VEC = UNIFORM && V > 1 && (EPT % V == 0);
     using vec_t = typename VecOf<CT>::type;
-    if (tl.full) {
+    if (tl.full && !P.umask) {
 #pragma unroll
         for (int k = 1; k <= NIN; ++k) {
             if (k < P.nops) {
@@ -157,14 +158,28 @@ SB_HD void map_phase1(const MapParams &P, const MapThread<NIN + 1> &th, const Ma
             }
         }
     } else {
-        const uint32_t rg = map_tile_rem(P, tl.id);
+        // masked tile: an edge tile (mask from the tile's remaining extents) or a balanced tile (plan-constant mask; whole
+        // 16-byte groups are valid or not, the planner keeps the balanced extents multiples of V)
+        const uint32_t rg = tl.full ? P.urg : map_tile_rem(P, tl.id);
 #pragma unroll
         for (int k = 1; k <= NIN; ++k) {
+            if (VEC && tl.full && k < P.nops && P.gvec[k]) {
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) {
-                CT x = make<CT>(0.0, 0.0);
-                if (k < P.nops && map_valid(P, th, rg, k, j)) x = load_elem<CT, UNIFORM>(tl.ptr[k] + P.g_joff[k][j], P.dtype[k], P.conj[k]);
-                v[k - 1][j] = x;
+                for (int j = 0; j < EPT; j += V) {
+                    vec_t x;
+#pragma unroll
+                    for (int u = 0; u < V; ++u) x.e[u] = make<CT>(0.0, 0.0);
+                    if (map_valid(P, th, rg, k, j)) x = *reinterpret_cast<const vec_t *>(tl.ptr[k] + P.g_joff[k][j]);
+#pragma unroll
+                    for (int u = 0; u < V; ++u) v[k - 1][j + u] = x.e[u];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < EPT; ++j) {
+                    CT x = make<CT>(0.0, 0.0);
+                    if (k < P.nops && map_valid(P, th, rg, k, j)) x = load_elem<CT, UNIFORM>(tl.ptr[k] + P.g_joff[k][j], P.dtype[k], P.conj[k]);
+                    v[k - 1][j] = x;
+                }
             }
         }
     }
@@ -205,6 +220,7 @@ SB_HD void map_phase2(const MapParams &P, const MapThread<NIN + 1> &th, const Ma
     unsigned char *ob = const_cast<unsigned char *>(tl.ptr[0]);
     constexpr int V = VecOf<CT>::V;
     constexpr bool VEC = UNIFORM && V > 1 && (EPT % V == 0);
+    const bool um = P.umask != 0;
     if (tl.full && VEC && P.gvec[0]) {
 #pragma unroll
         for (int j = 0; j < EPT; j += V) {
@@ -216,9 +232,9 @@ SB_HD void map_phase2(const MapParams &P, const MapThread<NIN + 1> &th, const Ma
                 for (int k = 0; k < NIN; ++k) a[k] = v[k][j + u];
                 x.e[u] = fn.template eval<NIN>(P.prog, a);
             }
-            store_vec16<CT>(ob + P.g_joff[0][j], x);
+            if (!um || map_valid(P, th, P.urg, 0, j)) store_vec16<CT>(ob + P.g_joff[0][j], x);
         }
-    } else if (tl.full) {
+    } else if (tl.full && !um) {
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
             CT a[NIN];
@@ -227,7 +243,7 @@ SB_HD void map_phase2(const MapParams &P, const MapThread<NIN + 1> &th, const Ma
             store_elem<CT, UNIFORM>(ob + P.g_joff[0][j], P.dtype[0], P.conj[0], fn.template eval<NIN>(P.prog, a));
         }
     } else {
-        const uint32_t rg = map_tile_rem(P, tl.id);
+        const uint32_t rg = tl.full ? P.urg : map_tile_rem(P, tl.id);
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
             CT a[NIN];

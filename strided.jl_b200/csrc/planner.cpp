@@ -539,6 +539,53 @@ void fill_common_tables(const OrderTab &o, int ept, int vbits, const uint8_t *cp
     }
 }
 
+// ---- hot-dims-first tile order -----------------------------------------------------------------------------
+// Tile ids count the output's dims in order (dim 0 fastest), so the CTAs of one wave write neighbouring output tiles --
+// but a transposing input's contiguous dim may be the SLOWEST-counted one (reversal `permutedims!(B, A, (4,3,2,1))` of
+// 91^4: the three tiles that share a 728-byte row of A run 12558 tiles apart): every 256-byte run is then fetched alone
+// from its DRAM page, and the sectors that straddle two tiles are fetched twice.  This order counts the hot dims (the
+// output's fastest dim, then every input's fastest dim) first, so that the tiles of one (output-fastest x input-fastest)
+// plane run in the same wave.
+bool build_hot_order(const MapParams &P, const bool *hot, std::vector<int32_t> &order)
+{
+    const int n = P.ndim;
+    if (P.ntiles > (1 << 22) || P.ntiles < 2) return false;
+    int perm[MAXD], np = 0;
+    for (int d = 0; d < n; ++d)
+        if (hot[d]) perm[np++] = d;
+    for (int d = 0; d < n; ++d)
+        if (!hot[d]) perm[np++] = d;
+    // identical to the natural order unless a multi-tile dim is overtaken by a later multi-tile dim
+    bool same = true;
+    {
+        int last = -1;
+        for (int s2 = 0; s2 < n; ++s2) {
+            if (P.ntile[perm[s2]] <= 1) continue;
+            if (perm[s2] < last) same = false;
+            last = perm[s2];
+        }
+    }
+    if (same) return false;
+    int64_t mul[MAXD], m = 1;
+    for (int d = 0; d < n; ++d) {
+        mul[d] = m;
+        m *= P.ntile[d];
+    }
+    order.resize((size_t)P.ntiles);
+    int32_t cc[MAXD] = {0};
+    for (int64_t pos = 0; pos < P.ntiles; ++pos) {
+        int64_t id = 0;
+        for (int d = 0; d < n; ++d) id += cc[d] * mul[d];
+        order[(size_t)pos] = (int32_t)id;
+        for (int s2 = 0; s2 < n; ++s2) {
+            const int d = perm[s2];
+            if (++cc[d] < P.ntile[d]) break;
+            cc[d] = 0;
+        }
+    }
+    return true;
+}
+
 // ---- alias-aware tile order ------------------------------------------------------------------------------
 // Inputs that are dim-permuted views of the SAME parent (A and A' in `(A .+ A') ./ 2`; the four rotations of
 // config 4) read every parent byte once per view.  The reference's answer is cache blocking inside one task;
@@ -1327,7 +1374,7 @@ bool plan_orbit(const Canon &c, const Program &prog, Plan &plan, const DeviceInf
     return true;
 }
 
-int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err)
+int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err, bool balanced = false)
 {
     MapParams &P = plan.map;
     std::memset(&P, 0, sizeof P);
@@ -1370,13 +1417,21 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
     // Tile extents are powers of two; an extent that does not divide the dim wastes masked lanes (profiles/
     // r01_v5_sweep_before_tilefix.txt: 70^4 ran at 0.18 of peak with 64-wide tiles).  lim[i] = the largest extent whose
     // padding waste ceil(n/b)*b/n stays <= 1.2 (never below a 32-byte run for hot dims).
+    // Balanced mode (MapParams::umask): a box of 2^bits holds ceil(dims / ntile) used coordinates; nothing is computed
+    // twice, the cost of a big box is its idle lanes -- "waste" is box / used extent, bounded by 1 / (lane utilisation).
+    auto bal_ext = [&](int i, int bits) {
+        const int64_t t = (int64_t)1 << bits;
+        const int64_t nt = (c.dims[i] + t - 1) / t;
+        return (c.dims[i] + nt - 1) / nt;
+    };
     auto waste_of = [&](int i, int bits) {
         const int64_t t = (int64_t)1 << bits;
+        if (balanced) return (double)t / (double)bal_ext(i, bits);
         return (double)(((c.dims[i] + t - 1) / t) * t) / (double)c.dims[i];
     };
     int lim[MAXD];
-    double max_waste = 1.2;
-    if (const char *e = std::getenv("SB_WASTE")) max_waste = std::max(1.0, std::atof(e)); // tuning knob
+    double max_waste = balanced ? 1.45 : 1.2;
+    if (const char *e = std::getenv(balanced ? "SB_BAL_WASTE" : "SB_WASTE")) max_waste = std::max(1.0, std::atof(e)); // tuning knob
     for (int i = 0; i < n; ++i) {
         const int lo = hot[i] ? std::min(cap[i], minrun_bits) : 0;
         int bbits = cap[i];
@@ -1486,9 +1541,27 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
     P.ept = ept;
     P.uniform = uniform;
     P.ntiles = 1;
+    // Balanced tiles (common.hpp MapParams::umask): the same number of tiles per dim, but each uses only
+    // ceil(dims / ntile) of the box's 2^tb coordinates (rounded up to whole 16-byte groups), so neighbouring tiles do not
+    // overlap and nothing is computed twice.
+    const int Vb = (uniform && esz < 16) ? 16 / esz : 1;
+    bool bal_vec_ok = true; // whole 16-byte groups are valid or not: every balanced extent is a multiple of V
     for (int i = 0; i < n; ++i) {
         P.dims[i] = c.dims[i];
         P.tile_b[i] = 1 << tb[i];
+        if (balanced && tb[i] > 0) {
+            const int64_t box = (int64_t)1 << tb[i];
+            int64_t ext = bal_ext(i, tb[i]);
+            if (ext % Vb != 0) {
+                const int64_t up = (ext + Vb - 1) / Vb * Vb;
+                if (up <= box && up <= c.dims[i]) ext = up;
+                else bal_vec_ok = false;
+            }
+            if (ext < box) {
+                P.tile_b[i] = (int32_t)ext;
+                P.umask = 1;
+            }
+        }
         const int64_t nt = (c.dims[i] + P.tile_b[i] - 1) / P.tile_b[i];
         if (nt > 0x7fffffff) { err = "dim too large"; return SB_E_UNSUPPORTED; }
         P.ntile[i] = (int32_t)nt;
@@ -1532,10 +1605,15 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
         }
     }
     P.guard = fill_cpos(ntd, tbits, P.cpos, P.cbits);
+    if (P.umask) {
+        int32_t ext[MAXTD];
+        for (int i = 0; i < ntd; ++i) ext[i] = P.tile_b[tdim[i]];
+        P.urg = pack_rem(ext, ntd, P.cpos, P.cbits, P.guard);
+    }
     // per-thread vector length: 16 bytes of the compute type when storage == compute type
     // measured (profiles/r01_v4_vector_experiment.txt): 128-bit accesses pay off for all-direct plans and for 4-byte
     // eltypes; for 8-byte staged plans the extra shared-memory conflicts of the 128-bit path cost more than they save
-    const bool want_vec = (P.nstaged == 0 || esz == 4) && !std::getenv("SB_NO_VEC");
+    const bool want_vec = (P.nstaged == 0 || esz == 4) && !std::getenv("SB_NO_VEC") && (!P.umask || bal_vec_ok);
     const int V = (uniform && esz < 16 && want_vec) ? 16 / esz : 1;
     const int vbits = (V > 1 && ept % V == 0) ? ilog2_ceil(V) : 0;
     P.vbits = vbits;
@@ -1548,8 +1626,11 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
 #endif
     auto aligned16 = [&](int k) {
         if (((uintptr_t)c.base[k] & 15u) != 0) return false;
-        for (int i = 0; i < n; ++i)
+        for (int i = 0; i < n; ++i) {
             if ((P.tstep[k][i] % 16) != 0) return false;
+            // (the shifted last tile starts `excess` elements before the regular grid position)
+            if (P.shift_last && P.excess[i] != 0 && ((int64_t)P.excess[i] * c.strides[k][i] * dtype_size(c.dtype[k])) % 16 != 0) return false;
+        }
         return true;
     };
     // functionals
@@ -1593,8 +1674,23 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
     plan.smem_bytes = (int64_t)smem_elems * esz;
     if (plan.smem_bytes > 200 * 1024) { err = "staging buffers exceed shared memory"; return SB_E_UNSUPPORTED; }
     plan.grid = std::min<int64_t>(P.ntiles, (int64_t)dev.sm_count * dev.ctas_per_sm);
-    if (build_tile_order(c, P, plan.tile_order)) plan.note = "alias-aware tile order";
-    const bool tma = plan_tma(c, P, tdim, plan, dev);
+    if (!P.umask && build_tile_order(c, P, plan.tile_order)) plan.note = "alias-aware tile order";
+    else {
+        plan.tile_order.clear();
+        if (P.nstaged > 0 && !std::getenv("SB_NO_HOT_ORDER") && build_hot_order(P, hot, plan.tile_order)) plan.note = "hot-dims-first tile order";
+    }
+    const bool tma = !P.umask && plan_tma(c, P, tdim, plan, dev); // (TMA boxes and the orbit cubes are whole power-of-two boxes)
+    if (plan.note == "hot-dims-first tile order") {
+        // measured (profiles/r02_q_hot_order.txt): reversal permutes on the LSU kernel gain 9-13 % (70^4 105.6 -> 92.8 us,
+        // 91^4 260.8 -> 233.9 us, 100^4 415.9 -> 360.8 us); the TMA ring loses 1-4 % (54^4, 64^4) and an L2-resident
+        // problem (41^4, 45 MB) loses the table lookup -- so only beyond L2 size and only for the LSU kernel
+        int64_t bytes = 0;
+        for (int k = 0; k < nops; ++k) bytes += elements * dtype_size(c.dtype[k]);
+        if (tma || bytes < ((int64_t)64 << 20)) {
+            plan.tile_order.clear();
+            plan.note.clear();
+        }
+    }
     if (tma) {
         // The TMA unit clips edge boxes for free, so pulling the last tile back only pays while the recomputed part is
         // small: 54^4 reversal, 10 of 54 columns twice: 35.3 us shifted vs 33.1 us masked; 4002^2: 45.6 vs 46.8 us.
@@ -1627,7 +1723,8 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
     }
     plan.elements = 1;
     for (int i = 0; i < n; ++i) plan.elements *= c.dims[i];
-    if (uniform && plan_orbit(c, P.prog, plan, dev)) plan.note = "alias-fused orbits";
+    if (uniform && !P.umask && plan_orbit(c, P.prog, plan, dev)) plan.note = "alias-fused orbits";
+    if (P.umask) plan.note = "balanced tiles";
     return SB_OK;
 }
 
@@ -1958,6 +2055,22 @@ int build_plan(const sb_desc &d, const DeviceInfo &dev, Plan &plan, std::string 
         }
     }
     rc = c.op == OP_NONE ? plan_map(c, dev, plan, err) : plan_reduce(c, dev, plan, err);
+    // Odd extents on the LSU kernel: power-of-two tiles with a shifted last tile recompute ntile*2^b / dims of every such
+    // dim.  Balanced tiles (MapParams::umask) remove the recomputation -- and measure the SAME or slower (reversal permute of
+    // 70^4: 105.9 us with 14-of-16 balanced tiles vs 105.6 us shifted; 130.5 us with 24-of-32 tiles;
+    // profiles/r02_q_odd_extents_balanced.txt): the kernel is bound by per-tile instruction issue and the latency of short
+    // unaligned runs, not by L2<->SM bytes.  Kept as an opt-in tuning knob (SB_BALANCED=1), off by default.
+    if (rc == SB_OK && plan.kind == PLAN_MAP && !plan.tma_ok && !plan.orbit_ok && std::getenv("SB_BALANCED")) {
+        const MapParams &P = plan.map;
+        double w_pow2 = 1.0; // work of the power-of-two tiling relative to the array (recomputed or masked coordinates)
+        for (int i = 0; i < P.ndim; ++i)
+            if (P.tile_b[i] > 1) w_pow2 *= (double)((int64_t)P.ntile[i] * P.tile_b[i]) / (double)c.dims[i];
+        if (w_pow2 > 1.10) {
+            Plan alt;
+            std::string err2;
+            if (plan_map(c, dev, alt, err2, true) == SB_OK && alt.map.umask) plan = std::move(alt);
+        }
+    }
     if (rc == SB_OK && c.depth > 4) {
         if (plan.key.recipe != RC_INTERP) { err = "internal: deep program matched a recipe"; return SB_E_INVALID; }
         plan.needs_jit = true;
@@ -1981,6 +2094,7 @@ std::string describe_plan(const Plan &p)
        << ",\"smem_bytes\":" << p.smem_bytes << ",\"elements\":" << p.elements;
     if (p.needs_jit) os << ",\"needs_jit\":1";
     if (p.kind == PLAN_MAP && p.map.shift_last) os << ",\"shift_last\":1";
+    if (p.kind == PLAN_MAP && p.map.umask) os << ",\"balanced\":1";
     auto arr64 = [&](const char *name, const int64_t *v, int n) {
         os << ",\"" << name << "\":[";
         for (int i = 0; i < n; ++i) os << (i ? "," : "") << v[i];

@@ -285,6 +285,35 @@ def edge_cases():
     return out
 
 
+# Odd extents (the reference's own tests use div(60, N)^N and 103; benchmarks/benchtests.jl sweeps 2^(2:1.5:20)): tiles that
+# do not divide the dims -- balanced / shifted / masked tiles --, padded parents whose strides ARE 16-byte multiples while
+# the extents are not (a shifted last tile then starts off the 16-byte grid), in-place updates (no recompute allowed).
+def odd_extent_cases():
+    out = []
+    for dt in (np.float64, np.float32, np.complex64):
+        rng = _rng("odd", np.dtype(dt).name)
+        nm = np.dtype(dt).name
+        for (m, n, ld) in ((71, 64, 72), (37, 129, 40), (103, 50, 104)):
+            a, b = randn(rng, ld * n + 8, dt), np.zeros(ld * n + 8, dt)
+            out.append(Case(f"odd_padded_copy_{m}x{n}_{nm}", [b, a], [ViewSpec(0, 0, (m, n), (1, ld)), ViewSpec(1, 0, (m, n), (1, ld))], P_COPY))
+            out.append(Case(f"odd_padded_off_{m}x{n}_{nm}", [b.copy(), a], [ViewSpec(0, 2, (m, n), (1, ld)), ViewSpec(1, 4, (m, n), (1, ld))],
+                            [K(3), A(0), F("mul")]))
+        for m in (41, 70, 91):
+            a, b = randn(rng, m * m, dt), np.zeros(m * m, dt)
+            out.append(Case(f"odd_transpose_{m}_{nm}", [b, a], [ViewSpec.dense(0, (m, m)), ViewSpec(1, 0, (m, m), (m, 1))], P_COPY))
+            out.append(Case(f"odd_A_plus_At_{m}_{nm}", [b.copy(), a], [ViewSpec.dense(0, (m, m)), ViewSpec.dense(1, (m, m)), ViewSpec(1, 0, (m, m), (m, 1))],
+                            [A(0), A(1), F("add"), K(2), F("div")]))
+            # in place: B .= B .+ A' (every element exactly once)
+            out.append(Case(f"odd_inplace_{m}_{nm}", [a.copy(), a], [ViewSpec.dense(0, (m, m)), ViewSpec.dense(0, (m, m)), ViewSpec(1, 0, (m, m), (m, 1))],
+                            [A(0), A(1), F("add")]))
+        for m in (13, 21):
+            sh = (m,) * 4
+            a, b = randn(rng, m ** 4, dt), np.zeros(m ** 4, dt)
+            for perm in ((3, 2, 1, 0), (1, 2, 3, 0), (2, 3, 0, 1)):
+                out.append(Case(f"odd_permute_{m}^4_{''.join(map(str, perm))}_{nm}", [b, a], [ViewSpec.dense(0, sh), ViewSpec.dense(1, sh).permutedims(perm)], P_COPY))
+    return out
+
+
 # README.md:85-89 / :133-137: the compute-bound benchmark expression  B .= A .* exp.(-2 .* A) .+ sin.(A .* A)
 # (the same parent captured four times: four identical views, nothing to fuse, one pass over A)
 def readme_compute_bound_cases(n=1000):
@@ -312,5 +341,6 @@ def all_cases(scale=1.0):
     cases += view_cases()
     cases += reduction_shape_cases(4 if s >= 1 else 1)
     cases += edge_cases()
+    cases += odd_extent_cases()
     cases += readme_compute_bound_cases(max(int(1000 * s), 64))
     return cases
