@@ -15,7 +15,7 @@ from tools.exp_orbit import time_variant  # noqa: E402
 CASES = {"rev41": lambda: case_c3(41), "rev54": lambda: case_c3(54), "rev70": lambda: case_c3(70), "rev91": lambda: case_c3(91), "rev100": lambda: case_c3(100),
          "rot70": lambda: case_c3(70, p=(1, 2, 3, 0)), "swap91": lambda: case_c3(91, p=(2, 3, 0, 1)), "c2_3001": lambda: case_c2(3001), "c1_1001": lambda: case_c1(1001), "c3_32": lambda: case_c3(32), "rev64": lambda: case_c3(64), "rot64": lambda: case_c3(64, p=(1, 2, 3, 0)),
          "rev128": lambda: case_c3(128)}
-VARS = [{}, {"SB_NO_HOT_ORDER": "1"}, {"SB_WASTE": "1.3"}, {"SB_WASTE": "1.4"}, {"SB_WASTE": "1.9"}]
+VARS = [{}, {"SB_FORCE_EPT": "16"}, {"SB_FORCE_EPT": "4"}]
 
 
 def main():

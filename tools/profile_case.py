@@ -18,6 +18,7 @@ from helpers import case_c1, case_c2, case_c3, case_c4, case_c5  # noqa: E402
 MAKE = {
     "c1": lambda: case_c1(1000), "c2": lambda: case_c2(4000), "c3": lambda: case_c3(32), "c4": lambda: case_c4(64),
     "c4p": lambda: case_c4(32, np.float64), "c4s": lambda: case_c4(16), "c4e": lambda: case_c4(20), "c2s": lambda: case_c2(512), "c5": lambda: case_c5(8, 4096), "c5shard": lambda: case_c5(1, 4096),
+    "rev91": lambda: case_c3(91), "rev70": lambda: case_c3(70), "c5small": lambda: case_c5(8, 512),
 }
 
 
