@@ -167,6 +167,7 @@ struct CachedPlan {
     Plan plan;
     void *dev_order = nullptr;
     void *dev_desc = nullptr;
+    void *dev_lsu = nullptr; // MapParams::lsu_desc
     void *dev_orbit = nullptr;
 };
 
@@ -221,6 +222,8 @@ static void clear_plans(sb_ctx *ctx)
         if (kv.second.dev_order) cudaFree(kv.second.dev_order);
     for (auto &kv : ctx->plans)
         if (kv.second.dev_desc) cudaFree(kv.second.dev_desc);
+    for (auto &kv : ctx->plans)
+        if (kv.second.dev_lsu) cudaFree(kv.second.dev_lsu);
     for (auto &kv : ctx->plans)
         if (kv.second.dev_orbit) cudaFree(kv.second.dev_orbit);
     ctx->plans.clear();
@@ -522,7 +525,7 @@ static int lookup_plan(sb_ctx *ctx, const sb_desc &desc, bool hostlink, PlanIt &
         if (ctx->plans.size() > 4096 && !stream_is_capturing(ctx)) clear_plans(ctx);
         CachedPlan cp;
         cp.plan = std::move(fresh);
-        const bool tables = !cp.plan.tile_order.empty() || !cp.plan.tile_desc.empty() || !cp.plan.orbit_items.empty();
+        const bool tables = !cp.plan.tile_order.empty() || !cp.plan.tile_desc.empty() || !cp.plan.orbit_items.empty() || !cp.plan.lsu_desc.empty();
         if (tables) {
             // plan tables live on the device with the plan.  Uploading them allocates and synchronises, which is illegal
             // while the stream is being captured into a CUDA graph: say so instead of invalidating the capture.
@@ -539,9 +542,11 @@ static int lookup_plan(sb_ctx *ctx, const sb_desc &desc, bool hostlink, PlanIt &
             if (!cp.plan.tile_order.empty()) e = upload(&cp.dev_order, cp.plan.tile_order.data(), cp.plan.tile_order.size() * sizeof(int32_t)); // alias-aware launch order
             if (e == cudaSuccess && !cp.plan.tile_desc.empty()) e = upload(&cp.dev_desc, cp.plan.tile_desc.data(), cp.plan.tile_desc.size() * sizeof(TileDesc)); // per-tile records of the TMA path
             if (e == cudaSuccess && !cp.plan.orbit_items.empty()) e = upload(&cp.dev_orbit, cp.plan.orbit_items.data(), cp.plan.orbit_items.size() * sizeof(OrbitItem)); // work items of the orbit kernel
+            if (e == cudaSuccess && !cp.plan.lsu_desc.empty()) e = upload(&cp.dev_lsu, cp.plan.lsu_desc.data(), cp.plan.lsu_desc.size() * sizeof(int64_t)); // per-tile records of the LSU kernel
             if (e != cudaSuccess) { // nothing half-built stays behind
                 if (cp.dev_order) cudaFree(cp.dev_order);
                 if (cp.dev_desc) cudaFree(cp.dev_desc);
+                if (cp.dev_lsu) cudaFree(cp.dev_lsu);
                 if (cp.dev_orbit) cudaFree(cp.dev_orbit);
                 return cuda_fail(ctx, e, "plan table upload");
             }
@@ -549,6 +554,8 @@ static int lookup_plan(sb_ctx *ctx, const sb_desc &desc, bool hostlink, PlanIt &
             cp.plan.tile_order.shrink_to_fit();
             cp.plan.tile_desc.clear();
             cp.plan.tile_desc.shrink_to_fit();
+            cp.plan.lsu_desc.clear();
+            cp.plan.lsu_desc.shrink_to_fit();
             cp.plan.orbit_items.clear();
             cp.plan.orbit_items.shrink_to_fit();
         }
@@ -570,6 +577,7 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc, const PeerLink *peer = nul
     Plan plan = hit->second.plan; // copy: bases are bound per call
     plan.map.tile_order = (const int32_t *)hit->second.dev_order;
     plan.map.tile_desc = (const TileDesc *)hit->second.dev_desc;
+    plan.map.lsu_desc = (const int64_t *)hit->second.dev_lsu;
     plan.orbit.items = (const OrbitItem *)hit->second.dev_orbit;
     for (int k = 0; k < MAXO; ++k) {
         plan.map.base[k] = (unsigned char *)desc.base[plan.base_src[k] < desc.nops ? plan.base_src[k] : 0];
@@ -580,6 +588,7 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc, const PeerLink *peer = nul
         // of the TMA variant were built for the shifted tiling)
         plan.map.shift_last = 0;
         plan.tma_ok = false;
+        plan.map.lsu_desc = nullptr; // (the records were built for the shifted tiling)
     }
     if (peer) {
         const bool can = plan.kind == PLAN_REDUCE && plan.red.nouttiles == 1 && plan.red.nout_tile <= PEER_MAX_OUT && plan.key.ct != C64 &&

@@ -24,11 +24,21 @@ template <class CT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forcein
     MapThread<NIN + 1> th;
     map_thread_init<NIN + 1>(P, t, th);
     const bool staged = P.nstaged > 0;
-    pdl_wait(); // first global access below
     const uint32_t ntiles = (uint32_t)P.ntiles;
+    // per-tile records (MapParams::lsu_desc) are written once, at plan creation: the first one is fetched before
+    // griddepcontrol.wait, the next one while the current tile is in flight
+    const bool pre = P.lsu_desc != nullptr && P.lsu_prefetch != 0;
+    int64_t rec[NIN + 2];
+    if (pre && blockIdx.x < ntiles) map_tile_record<NIN + 1>(P, blockIdx.x, rec);
+    pdl_wait(); // first access to operand memory below
     for (uint32_t pos = blockIdx.x; pos < ntiles; pos += gridDim.x) {
         MapTile<NIN + 1> tl;
-        map_tile_init<NIN + 1>(P, th, pos, tl);
+        if (pre) {
+            map_tile_from_record<NIN + 1>(P, th, rec, tl);
+            if (pos + gridDim.x < ntiles) map_tile_record<NIN + 1>(P, pos + gridDim.x, rec);
+        } else {
+            map_tile_init<NIN + 1>(P, th, pos, tl);
+        }
         CT v[NIN][EPT];
         map_phase1<CT, NIN, EPT, UNIFORM>(P, th, tl, t, v, sb_smem_raw);
         if (staged) __syncthreads();

@@ -59,8 +59,30 @@ template <int NOPS> SB_HD void map_thread_init(const MapParams &P, int t, MapThr
     }
 }
 
+// per-tile record of launch position `pos` (MapParams::lsu_desc): nops + 1 words
+template <int NOPS> SB_HD void map_tile_record(const MapParams &P, uint32_t pos, int64_t (&r)[NOPS + 1])
+{
+    const int64_t *src = P.lsu_desc + (size_t)pos * (size_t)(P.nops + 1);
+#pragma unroll
+    for (int k = 0; k <= NOPS; ++k) r[k] = k <= P.nops ? src[k] : 0;
+}
+template <int NOPS> SB_HD void map_tile_from_record(const MapParams &P, const MapThread<NOPS> &th, const int64_t (&r)[NOPS + 1], MapTile<NOPS> &tl)
+{
+    const uint32_t w = (uint32_t)r[0];
+    tl.id = w & 0x7fffffffu;
+    tl.full = (w >> 31) != 0;
+#pragma unroll
+    for (int k = 0; k < NOPS; ++k) tl.ptr[k] = P.base[k < P.nops ? k : 0] + (th.g_toff[k] + (k < P.nops ? r[1 + k] : 0));
+}
+
 template <int NOPS> SB_HD void map_tile_init(const MapParams &P, const MapThread<NOPS> &th, uint32_t pos, MapTile<NOPS> &tl)
 {
+    if (P.lsu_desc) { // precomputed record (planner.cpp, "per-tile records for the LSU kernel"): same values as the decode below
+        int64_t r[NOPS + 1];
+        map_tile_record<NOPS>(P, pos, r);
+        map_tile_from_record<NOPS>(P, th, r, tl);
+        return;
+    }
     uint32_t id = P.tile_order ? (uint32_t)P.tile_order[pos] : pos;
     tl.id = id;
     int64_t off[NOPS];

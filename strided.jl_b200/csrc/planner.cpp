@@ -1721,6 +1721,31 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
             if (full) td.id_full |= 0x80000000u;
         }
     }
+    // per-tile records for the LSU kernel (MapParams::lsu_desc): multi-dim plans with enough tiles to pay for the table
+    int64_t lsu_min_tiles = 256;
+    if (const char *e = std::getenv("SB_LSU_DESC_MIN")) lsu_min_tiles = std::max<int64_t>(1, std::atoll(e)); // (tests: exercise the table on small cases)
+    if (!tma && n >= 2 && P.ntiles >= lsu_min_tiles && P.ntiles * (int64_t)(nops + 1) * 8 <= ((int64_t)8 << 20) && !std::getenv("SB_NO_LSU_DESC")) {
+        const int W = nops + 1;
+        P.lsu_prefetch = std::getenv("SB_LSU_NO_PREFETCH") ? 0 : 1;
+        plan.lsu_desc.resize((size_t)P.ntiles * (size_t)W);
+        for (int64_t pos = 0; pos < P.ntiles; ++pos) {
+            uint32_t id = plan.tile_order.empty() ? (uint32_t)pos : (uint32_t)plan.tile_order[(size_t)pos];
+            int64_t *r = &plan.lsu_desc[(size_t)pos * (size_t)W];
+            uint32_t w = id;
+            bool full = true;
+            for (int k = 0; k < nops; ++k) r[1 + k] = 0;
+            for (int d = 0; d < n; ++d) {
+                const uint32_t cd = id % (uint32_t)P.ntile[d];
+                id /= (uint32_t)P.ntile[d];
+                const bool shifted = P.shift_last && P.excess[d] != 0 && (int32_t)cd == P.ntile[d] - 1;
+                full = full && (shifted || (int32_t)cd < P.nfull[d]);
+                for (int k = 0; k < nops; ++k)
+                    r[1 + k] += (int64_t)cd * P.tstep[k][d] - (shifted ? (int64_t)P.excess[d] * P.strides[k][d] * dtype_size(P.dtype[k]) : 0);
+            }
+            if (full) w |= 0x80000000u;
+            r[0] = (int64_t)w;
+        }
+    }
     plan.elements = 1;
     for (int i = 0; i < n; ++i) plan.elements *= c.dims[i];
     if (uniform && !P.umask && plan_orbit(c, P.prog, plan, dev)) plan.note = "alias-fused orbits";
@@ -2095,6 +2120,7 @@ std::string describe_plan(const Plan &p)
     if (p.needs_jit) os << ",\"needs_jit\":1";
     if (p.kind == PLAN_MAP && p.map.shift_last) os << ",\"shift_last\":1";
     if (p.kind == PLAN_MAP && p.map.umask) os << ",\"balanced\":1";
+    if (p.kind == PLAN_MAP && !p.lsu_desc.empty()) os << ",\"lsu_desc\":1";
     auto arr64 = [&](const char *name, const int64_t *v, int n) {
         os << ",\"" << name << "\":[";
         for (int i = 0; i < n; ++i) os << (i ? "," : "") << v[i];

@@ -404,9 +404,11 @@ extern "C" int emul_mapreduce(const sb_desc *desc, int grid_limit)
         return SB_E_UNSUPPORTED;
     }
     if (!plan.tile_order.empty()) plan.map.tile_order = plan.tile_order.data();
+    if (!plan.lsu_desc.empty()) plan.map.lsu_desc = plan.lsu_desc.data();
     if (plan.kind == PLAN_MAP && plan.map.shift_last && output_overlaps_inputs(*desc)) { // as the launch does (csrc/abi.cu)
         plan.map.shift_last = 0;
         plan.tma_ok = false;
+        plan.map.lsu_desc = nullptr;
     }
     bool ok = false;
     if (plan.kind == PLAN_MAP) {

@@ -34,3 +34,19 @@ def test_golden_fixtures_through_the_emulated_kernels():
         z = np.load(os.path.join(gdir, f), allow_pickle=False)
         case = Case.from_npz(z)
         case.assert_close(case.run_emul(), z["expected"], exact=bool(z["exact"]))
+
+
+def test_emulated_lsu_tile_records(monkeypatch):
+    """per-tile records of the LSU map kernel (MapParams::lsu_desc): the table is built from 512 tiles on; here it is forced
+    on every multi-dim map plan and must give the results of the in-kernel decode (edge tiles, shifted tiles, in-place
+    updates that drop the table at bind time, tile orders)."""
+    monkeypatch.setenv("SB_LSU_DESC_MIN", "1")
+    monkeypatch.setenv("SB_NO_TMA", "1")
+    seen = 0
+    for case in cases.all_cases(0.3):
+        if case.op != 0:
+            continue
+        if case.plan().get("lsu_desc"):
+            seen += 1
+        case.assert_close(case.run_emul(grid_limit=3), case.expected())
+    assert seen > 50

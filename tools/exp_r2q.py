@@ -15,7 +15,7 @@ from tools.exp_orbit import time_variant  # noqa: E402
 CASES = {"rev41": lambda: case_c3(41), "rev54": lambda: case_c3(54), "rev70": lambda: case_c3(70), "rev91": lambda: case_c3(91), "rev100": lambda: case_c3(100),
          "rot70": lambda: case_c3(70, p=(1, 2, 3, 0)), "swap91": lambda: case_c3(91, p=(2, 3, 0, 1)), "c2_3001": lambda: case_c2(3001), "c1_1001": lambda: case_c1(1001), "c3_32": lambda: case_c3(32), "rev64": lambda: case_c3(64), "rot64": lambda: case_c3(64, p=(1, 2, 3, 0)),
          "rev128": lambda: case_c3(128)}
-VARS = [{}, {"SB_FORCE_EPT": "16"}, {"SB_FORCE_EPT": "4"}]
+VARS = [{}, {"SB_LSU_NO_PREFETCH": "1"}, {"SB_NO_LSU_DESC": "1"}]
 
 
 def main():
@@ -33,7 +33,7 @@ def main():
                 if first is None:
                     first = got
                 print(f"{nm} env={env} us={us:.2f} GB/s={nbytes / us * 1e-3:.0f} frac={nbytes / us * 1e-3 / 6545.9:.3f} same={bool(np.array_equal(got, first))} tile={p.get('tile')} "
-                      f"bal={p.get('balanced')} tma={p.get('tma')} order={p.get('tile_order')} shift={p.get('shift_last')} ept={p.get('ept')}", flush=True)
+                      f"bal={p.get('balanced')} tma={p.get('tma')} lsu_desc={p.get('lsu_desc')} order={p.get('tile_order')} shift={p.get('shift_last')} ept={p.get('ept')}", flush=True)
             except Exception as e:
                 print(f"{nm} env={env} ERROR {e}", flush=True)
         del dev
