@@ -794,12 +794,12 @@ static void desc_ranges(const sb_desc &d, uintptr_t (&lo)[SB_MAX_OPS], uintptr_t
 static bool group_plan_ok(sb_ctx *ctx, const CachedPlan &cp)
 {
     const Plan &pl = cp.plan;
-    if (pl.kind != PLAN_MAP || !pl.tma_ok || pl.needs_jit || pl.tma.nin > TMA_GROUP_MAXIN) return false;
+    (void)ctx;
+    if (pl.kind != PLAN_MAP || pl.needs_jit || env_cache().no_group) return false;
     if (pl.orbit_ok && cp.dev_orbit) return false;
     if (pl.key.recipe == RC_INTERP && jit_enabled() && pl.elements >= (int64_t)env_cache().jit_min_elements) return false; // NVRTC-specialised kernel
-    if (env_cache().no_group) return false;
-    (void)ctx;
-    return find_tma_group_kernel(pl.key) != nullptr;
+    if (pl.tma_ok) return pl.tma.nin <= TMA_GROUP_MAXIN && find_tma_group_kernel(pl.key) != nullptr;
+    return find_map_group_kernel(pl.key) != nullptr; // LSU kernel
 }
 
 static int run_group(sb_ctx *ctx, const sb_desc *descs, const int *idx, int cnt, const CachedPlan &cp, bool *done)
@@ -808,28 +808,58 @@ static int run_group(sb_ctx *ctx, const sb_desc *descs, const int *idx, int cnt,
     Plan plan = cp.plan;
     plan.map.tile_order = (const int32_t *)cp.dev_order;
     plan.map.tile_desc = (const TileDesc *)cp.dev_desc;
-    const TmaGroupEntry *gk = find_tma_group_kernel(plan.key);
-    if (!gk) return SB_OK;
-    TmaGroup G;
-    std::memset(&G, 0, sizeof G);
-    G.nprob = cnt;
-    for (int p = 0; p < cnt; ++p) {
-        const sb_desc &d = descs[idx[p]];
-        if (plan.map.shift_last && output_overlaps_inputs(d)) return SB_OK; // in-place update: masked edge tiles, LSU kernel
+    plan.map.lsu_desc = (const int64_t *)cp.dev_lsu;
+    for (int p = 0; p < cnt; ++p)
+        if (plan.map.shift_last && output_overlaps_inputs(descs[idx[p]])) return SB_OK; // in-place update: masked edge tiles, one by one
+    auto bind = [&](const sb_desc &d) {
         for (int k = 0; k < MAXO; ++k) plan.map.base[k] = (unsigned char *)d.base[plan.base_src[k] < d.nops ? plan.base_src[k] : 0];
-        alignas(64) CUtensorMap maps[TMA_MAXIN];
-        if (!encode_tma_maps(plan, maps)) return SB_OK;
-        for (int k = 0; k < TMA_GROUP_MAXIN; ++k) G.maps[p][k] = maps[k < plan.tma.nin ? k : 0];
-        G.out[p] = plan.map.base[0];
-    }
+    };
     cudaSetDevice(ctx->device);
-    int nb = 1;
-    int rc = occupancy_of(ctx, gk->func, gk->occupancy, (size_t)plan.tma_smem_bytes, nb);
-    if (rc != SB_OK) return rc;
-    int64_t grid = std::min<int64_t>(plan.map.ntiles * cnt, (int64_t)ctx->dev.sm_count * nb);
-    if (grid < 1) grid = 1;
-    cudaError_t e = gk->launch(plan.map, plan.tma, G, (int)grid, (size_t)plan.tma_smem_bytes, ctx->stream);
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "map_tma_group launch");
+    if (plan.tma_ok) {
+        const TmaGroupEntry *gk = find_tma_group_kernel(plan.key);
+        if (!gk) return SB_OK;
+        TmaGroup G;
+        std::memset(&G, 0, sizeof G);
+        G.nprob = cnt;
+        for (int p = 0; p < cnt; ++p) {
+            bind(descs[idx[p]]);
+            alignas(64) CUtensorMap maps[TMA_MAXIN];
+            if (!encode_tma_maps(plan, maps)) return SB_OK;
+            for (int k = 0; k < TMA_GROUP_MAXIN; ++k) G.maps[p][k] = maps[k < plan.tma.nin ? k : 0];
+            G.out[p] = plan.map.base[0];
+        }
+        int nb = 1;
+        int rc = occupancy_of(ctx, gk->func, gk->occupancy, (size_t)plan.tma_smem_bytes, nb);
+        if (rc != SB_OK) return rc;
+        int64_t grid = std::min<int64_t>(plan.map.ntiles * cnt, (int64_t)ctx->dev.sm_count * nb);
+        if (grid < 1) grid = 1;
+        cudaError_t e = gk->launch(plan.map, plan.tma, G, (int)grid, (size_t)plan.tma_smem_bytes, ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "map_tma_group launch");
+    } else {
+        const MapGroupEntry *gk = find_map_group_kernel(plan.key);
+        if (!gk) return SB_OK;
+        MapGroup G;
+        std::memset(&G, 0, sizeof G);
+        G.nprob = cnt;
+        unsigned char *base0[MAXO];
+        bind(descs[idx[0]]);
+        for (int k = 0; k < MAXO; ++k) base0[k] = plan.map.base[k];
+        for (int p = 0; p < cnt; ++p) {
+            bind(descs[idx[p]]);
+            for (int k = 0; k < MAXO; ++k) {
+                // (128-bit accesses were planned from problem 0's alignment: the key carries base & 15 per operand, so every problem of the plan agrees)
+                G.delta[p][k] = (int64_t)((intptr_t)plan.map.base[k] - (intptr_t)base0[k]);
+            }
+        }
+        for (int k = 0; k < MAXO; ++k) plan.map.base[k] = base0[k];
+        int nb = 1;
+        int rc = occupancy_of(ctx, gk->func, gk->occupancy, (size_t)plan.smem_bytes, nb);
+        if (rc != SB_OK) return rc;
+        int64_t grid = std::min<int64_t>(plan.map.ntiles * cnt, (int64_t)ctx->dev.sm_count * nb);
+        if (grid < 1) grid = 1;
+        cudaError_t e = gk->launch(plan.map, G, (int)grid, (size_t)plan.smem_bytes, ctx->stream);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "map_tile_group launch");
+    }
     ctx->stats.launches++;
     ctx->stats.grouped_calls += (uint64_t)cnt;
     *done = true;
@@ -904,7 +934,7 @@ extern "C" int sb_mapreduce_batch(sb_ctx *ctx, int n, const sb_desc *descs)
             u.idx.push_back(i);
             taken[i] = 1;
             if (cps[i]) {
-                for (int j = i + 1; j < n && (int)u.idx.size() < TMA_GROUP_MAX; ++j)
+                for (int j = i + 1; j < n && (int)u.idx.size() < (TMA_GROUP_MAX < MAP_GROUP_MAX ? TMA_GROUP_MAX : MAP_GROUP_MAX); ++j)
                     if (parallel[j] && !taken[j] && cps[j] == cps[i]) {
                         u.idx.push_back(j);
                         taken[j] = 1;

@@ -226,6 +226,15 @@ struct MapParams {
     Program prog;
 };
 
+// Several problems of ONE map plan in one launch of the LSU kernel (sb_mapreduce_batch): problem p's operand k lives
+// `delta[p][k]` bytes from problem 0's (whose bases are MapParams::base); launch position g = p * ntiles + tile.
+constexpr int MAP_GROUP_MAX = 16;
+struct MapGroup {
+    int32_t nprob;
+    int32_t pad_;
+    int64_t delta[MAP_GROUP_MAX][MAXO];
+};
+
 // ---- TMA-staged map plan ------------------------------------------------------------------------------------
 // Same tile decomposition as MapParams, but every INPUT tile is fetched by the Tensor Memory Accelerator
 // (cp.async.bulk.tensor) into a multi-stage shared-memory ring, several tiles ahead of the consumers.

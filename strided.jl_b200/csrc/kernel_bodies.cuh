@@ -16,7 +16,8 @@ template <class CT, int NIN, int EPT> struct MinBlocks {
     static constexpr int value = words <= 32 ? 4 : (words <= 64 ? 2 : 1);
 };
 
-template <class CT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forceinline__ void map_tile_body(const MapParams &P)
+template <class CT, int RC, int NIN, int EPT, bool UNIFORM, bool GROUP>
+__device__ __forceinline__ void map_tile_body_impl(const MapParams &P, const MapGroup *G)
 {
     extern __shared__ __align__(16) unsigned char sb_smem_raw[];
     const int t = threadIdx.x;
@@ -24,20 +25,32 @@ template <class CT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forcein
     MapThread<NIN + 1> th;
     map_thread_init<NIN + 1>(P, t, th);
     const bool staged = P.nstaged > 0;
-    const uint32_t ntiles = (uint32_t)P.ntiles;
+    const uint32_t ntiles1 = (uint32_t)P.ntiles;                              // tiles of one problem
+    const uint32_t ntiles = GROUP ? ntiles1 * (uint32_t)G->nprob : ntiles1;  // positions of this launch
     // per-tile records (MapParams::lsu_desc) are written once, at plan creation: the first one is fetched before
     // griddepcontrol.wait, the next one while the current tile is in flight
     const bool pre = P.lsu_desc != nullptr && P.lsu_prefetch != 0;
     int64_t rec[NIN + 2];
-    if (pre && blockIdx.x < ntiles) map_tile_record<NIN + 1>(P, blockIdx.x, rec);
+    if (pre && blockIdx.x < ntiles) map_tile_record<NIN + 1>(P, GROUP ? blockIdx.x % ntiles1 : blockIdx.x, rec);
     pdl_wait(); // first access to operand memory below
-    for (uint32_t pos = blockIdx.x; pos < ntiles; pos += gridDim.x) {
+    for (uint32_t gpos = blockIdx.x; gpos < ntiles; gpos += gridDim.x) {
+        uint32_t pos = gpos, prob = 0;
+        if (GROUP) {
+            prob = gpos / ntiles1;
+            pos = gpos - prob * ntiles1;
+        }
         MapTile<NIN + 1> tl;
         if (pre) {
             map_tile_from_record<NIN + 1>(P, th, rec, tl);
-            if (pos + gridDim.x < ntiles) map_tile_record<NIN + 1>(P, pos + gridDim.x, rec);
+            const uint32_t nx = gpos + gridDim.x;
+            if (nx < ntiles) map_tile_record<NIN + 1>(P, GROUP ? nx % ntiles1 : nx, rec);
         } else {
             map_tile_init<NIN + 1>(P, th, pos, tl);
+        }
+        if (GROUP) {
+#pragma unroll
+            for (int k = 0; k <= NIN; ++k)
+                if (k < P.nops) tl.ptr[k] += G->delta[prob][k];
         }
         CT v[NIN][EPT];
         map_phase1<CT, NIN, EPT, UNIFORM>(P, th, tl, t, v, sb_smem_raw);
@@ -45,6 +58,10 @@ template <class CT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forcein
         map_phase2<CT, RC, NIN, EPT, UNIFORM>(P, th, tl, t, v, sb_smem_raw);
         if (staged) __syncthreads();
     }
+}
+template <class CT, int RC, int NIN, int EPT, bool UNIFORM> __device__ __forceinline__ void map_tile_body(const MapParams &P)
+{
+    map_tile_body_impl<CT, RC, NIN, EPT, UNIFORM, false>(P, nullptr);
 }
 
 // ---- fused exchange across GPUs (peer group) ---------------------------------------------------------------

@@ -46,6 +46,11 @@ __global__ void __launch_bounds__(THREADS, MinBlocks<CT, NIN, EPT>::value) map_t
 {
     map_tile_body<CT, RC, NIN, EPT, UNIFORM>(P);
 }
+template <class CT, int RC, int NIN, int EPT, bool UNIFORM>
+__global__ void __launch_bounds__(THREADS, MinBlocks<CT, NIN, EPT>::value) map_tile_group_kernel(const __grid_constant__ MapParams P, const __grid_constant__ MapGroup G)
+{
+    map_tile_body_impl<CT, RC, NIN, EPT, UNIFORM, true>(P, &G);
+}
 template <class AT, int RC, int NIN, int EPT, bool UNIFORM>
 __global__ void __launch_bounds__(THREADS, MinBlocks<AT, NIN, EPT>::value) reduce_tile_kernel(const __grid_constant__ ReduceParams P)
 {
@@ -92,6 +97,39 @@ template <class CT, int RC, int NIN, int EPT, bool U> struct MapLaunch {
     }
     static const void *func() { return (const void *)map_tile_kernel<CT, RC, NIN, EPT, U>; }
 };
+
+// grouped launches of the LSU map kernel (kernels_map_group.cu: a small set of recipes)
+struct MapGroupEntry {
+    KernelKey key;
+    cudaError_t (*launch)(const MapParams &, const MapGroup &, int grid, size_t smem, cudaStream_t);
+    cudaError_t (*occupancy)(int *nblocks, size_t smem);
+    const void *func;
+};
+template <class CT, int RC, int NIN, int EPT, bool U> struct MapGroupLaunch {
+    static cudaError_t launch(const MapParams &P, const MapGroup &G, int grid, size_t smem, cudaStream_t s)
+    {
+        auto k = map_tile_group_kernel<CT, RC, NIN, EPT, U>;
+        if (smem > 48 * 1024) {
+            cudaError_t e = ensure_dynamic_smem((const void *)k, smem);
+            if (e != cudaSuccess) return e;
+        }
+        return launch_pdl(k, grid, THREADS, smem, s, P, G);
+    }
+    static cudaError_t occupancy(int *nb, size_t smem)
+    {
+        auto k = map_tile_group_kernel<CT, RC, NIN, EPT, U>;
+        if (smem > 48 * 1024) {
+            cudaError_t e = ensure_dynamic_smem((const void *)k, smem);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, THREADS, smem);
+    }
+    static const void *func() { return (const void *)map_tile_group_kernel<CT, RC, NIN, EPT, U>; }
+};
+#define SB_MAP_GROUP_ENTRY(CT, DT, RC, NIN, EPT)                                                                     \
+    MapGroupEntry { KernelKey{DT, RC, NIN, EPT, 1}, &MapGroupLaunch<CT, RC, NIN, EPT, true>::launch,                 \
+                    &MapGroupLaunch<CT, RC, NIN, EPT, true>::occupancy, MapGroupLaunch<CT, RC, NIN, EPT, true>::func() }
+const MapGroupEntry *find_map_group_kernel(const KernelKey &k);
 
 template <class AT, int RC, int NIN, int EPT, bool U> struct ReduceLaunch {
     static cudaError_t launch(const ReduceParams &P, int grid, size_t smem, cudaStream_t s)

@@ -1476,7 +1476,14 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
     // Small transposing problems (BASELINE configs 1 and 3: 1000^2 `3 .* A'`, 32^4 permutedims) keep the 2048-element
     // tile of the TMA ring kernel instead of shrinking to 1024 elements for the LSU kernel: measured 4.5 -> 3.9 us
     // (config 3) and 5.9 -> 4.1 us (config 1), profiles/r02_a_exp.txt.
-    if (ept < 8 && !std::getenv("SB_FORCE_EPT") && tma_candidate(c, P.prog.recipe, template_nin(P.prog.recipe, nin), uniform)) ept = 8;
+    // With per-tile records (MapParams::lsu_desc) the LSU kernel beats the TMA ring on SINGLE-input transposes in two cases
+    // (profiles/r02_v_tma_vs_lsu_with_records.txt): small problems (one or two waves: 32^4 permutedims 4.03 -> 3.40 us,
+    // 1000^2 `3 .* A'` 3.72 -> 3.42 us) and tilings without edge tiles (64^4 48.3 -> 45.3 us, 96^4 257.8 -> 222.6 us, 128^4
+    // 835 -> 697 us = 0.94 of peak).  The TMA ring keeps two-input maps (`(A .+ A') ./ 2`: 42.4 vs 46.3 us) and extents that
+    // leave edge tiles, which the TMA unit clips for free (54^4: 31.9 vs 50.9 us; 3000^2: 24.7 vs 26.2 us).
+    const bool lsu_pref_on = !std::getenv("SB_NO_PREFER_LSU") && !std::getenv("SB_NO_LSU_DESC") && nin == 1 && esz == 8;
+    const bool small_single = lsu_pref_on && elements * esz * 2 <= ((int64_t)32 << 20);
+    if (ept < 8 && !std::getenv("SB_FORCE_EPT") && !small_single && tma_candidate(c, P.prog.recipe, template_nin(P.prog.recipe, nin), uniform)) ept = 8;
     if (!std::getenv("SB_FORCE_EPT")) { // prefer the largest tile that can be filled without padding waste
         int best = ept, best_left = 1 << 30;
         for (int e = ept; e >= 4; e /= 2) {
@@ -1679,7 +1686,10 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
         plan.tile_order.clear();
         if (P.nstaged > 0 && !std::getenv("SB_NO_HOT_ORDER") && build_hot_order(P, hot, plan.tile_order)) plan.note = "hot-dims-first tile order";
     }
-    const bool tma = !P.umask && plan_tma(c, P, tdim, plan, dev); // (TMA boxes and the orbit cubes are whole power-of-two boxes)
+    bool exact_tiling = true;
+    for (int i = 0; i < n; ++i) exact_tiling = exact_tiling && (c.dims[i] % P.tile_b[i] == 0);
+    const bool prefer_lsu = small_single || (lsu_pref_on && exact_tiling);
+    const bool tma = !P.umask && !prefer_lsu && plan_tma(c, P, tdim, plan, dev); // (TMA boxes and the orbit cubes are whole power-of-two boxes)
     if (plan.note == "hot-dims-first tile order") {
         // measured (profiles/r02_q_hot_order.txt): reversal permutes on the LSU kernel gain 9-13 % (70^4 105.6 -> 92.8 us,
         // 91^4 260.8 -> 233.9 us, 100^4 415.9 -> 360.8 us); the TMA ring loses 1-4 % (54^4, 64^4) and an L2-resident

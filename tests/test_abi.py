@@ -51,11 +51,19 @@ def test_plans_for_baseline_configs():
     assert p["tile"] == [64, 32] and p["staged"] == [0, 0, 1] and p["ntiles"] == 63 * 125
     assert p["tile_order"] == 1  # A and A' alias: tiles (I,J),(J,I) are launched side by side
     assert p["tma"] >= 2  # the TMA ring kernel
+    # single-input transposes: small problems and tilings without edge tiles take the LSU kernel with per-tile records
+    # (faster than the TMA ring there, profiles/r02_v_tma_vs_lsu_with_records.txt); edge tiles keep the TMA ring
     p = case_c1(1000).plan()
     assert p["recipe"] == "scale" and p["staged"] == [0, 1] and p["tile_order"] == 0
-    assert p["tma"] == 2 and p["ept"] == 8  # the permutedims/transpose case goes through the TMA ring at every size
-    p = case_c3(32).plan()  # one-wave problem: 2048-element tiles of the TMA ring kernel, two stages
-    assert p["recipe"] == "copy" and p["dims"] == [32, 32, 32, 32] and p["tile"] == [32, 2, 1, 32] and p["ept"] == 8 and p["tma"] == 2
+    assert p["tma"] == 0 and p["ept"] == 4 and p["tile"] == [32, 32] and p["lsu_desc"] == 1
+    p = case_c3(32).plan()
+    assert p["recipe"] == "copy" and p["dims"] == [32, 32, 32, 32] and p["tile"] == [32, 1, 1, 32] and p["ept"] == 4 and p["tma"] == 0 and p["lsu_desc"] == 1
+    p = case_c3(128).plan()  # large, no edge tiles: LSU
+    assert p["tma"] == 0 and p["lsu_desc"] == 1 and p["ept"] == 8
+    p = case_c3(54).plan()   # 54 = 0.84 of a 64-wide tile: the TMA unit clips edge boxes for free
+    assert p["tma"] >= 2
+    p = case_c1(3000).plan()
+    assert p["tma"] >= 2
     p = case_c5(1, 4096).plan()  # per-GPU share of config 5: one dense run -> streamed complete reduction
     assert p["dims"] == [16777216] and p["stream"]["grid"] == 148 and p["stream"]["chunk_bytes"] == 32768 and p["stream"]["nstage"] == 4
     p = case_c4(64).plan()
