@@ -129,7 +129,8 @@ def run_all(eng, peak):
             ms = _time(lambda i: sb.run_batch(batches[i % len(batches)]), 10 * len(batches)) / nb
             out.append(_entry(f"C3 f64 {m}^4 permutedims (4,3,2,1) x{nb} in one batch (rot, per problem)", 2 * m ** 4 * 8, ms, peak, batch=nb,
                               launches_per_batch=st["launches"], grouped_calls=st["grouped_calls"],
-                              kernel=f"sb_mapreduce_batch, {st['launches']} grouped launch(es) for {nb} calls: " + _kernel([], 0, 0, shape, list(pairs[0]))))
+                              kernel=f"sb_mapreduce_batch: {st['launches']} grouped launch(es) for {nb} calls (map_tile_group_kernel, the group's plan is sized for all "
+                                     f"problems: 2048-element tiles, per-tile records); a single call of this shape runs " + _kernel([], 0, 0, shape, list(pairs[0]))))
         # the size-matched yardstick: a dense copy of the same 16.8 MB through the engine (what launch + ramp + drain cost
         # at this size, whatever the access pattern)
         dense = [(sb.StridedView(Bs[i]), sb.StridedView(As[i])) for i in range(k)]

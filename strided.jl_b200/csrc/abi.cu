@@ -470,7 +470,7 @@ typedef std::unordered_map<std::string, CachedPlan>::iterator PlanIt;
 // of device work, so planning must not be on the critical path).  `hostlink`: the operands live in pinned HOST memory and
 // are read / written by the kernel itself (zero-copy mode of sb_mapreduce_host): the planner then fuses aliased views
 // from two views on, because every byte that crosses the host link twice costs twice.
-static int lookup_plan(sb_ctx *ctx, const sb_desc &desc, bool hostlink, PlanIt &hit)
+static int lookup_plan(sb_ctx *ctx, const sb_desc &desc, bool hostlink, PlanIt &hit, bool grouped = false)
 {
     sb_desc keyd;
     std::memset(&keyd, 0, sizeof keyd); // field-wise copy below: struct padding must not leak into the key
@@ -512,6 +512,7 @@ static int lookup_plan(sb_ctx *ctx, const sb_desc &desc, bool hostlink, PlanIt &
     for (int i = (keyd.ntok > 0 ? keyd.ntok : 0); i < SB_MAX_TOKENS; ++i) keyd.prog[i] = sb_tok{0, 0, 0.0, 0.0};
     std::string key((const char *)&keyd, sizeof keyd);
     key.push_back(hostlink ? 'H' : 'D');
+    if (grouped) key.push_back('G'); // plan for a grouped launch (sb_mapreduce_batch): sized for many problems of this shape
     int rc;
     hit = ctx->plans.find(key);
     if (hit == ctx->plans.end()) {
@@ -519,6 +520,7 @@ static int lookup_plan(sb_ctx *ctx, const sb_desc &desc, bool hostlink, PlanIt &
         std::string err;
         DeviceInfo dinfo = ctx->dev;
         dinfo.host_link = hostlink;
+        dinfo.grouped = grouped;
         rc = build_plan(desc, dinfo, fresh, err);
         if (rc != SB_OK) return set_err(ctx, rc, err);
         ctx->stats.plans_built++;
@@ -925,7 +927,7 @@ extern "C" int sb_mapreduce_batch(sb_ctx *ctx, int n, const sb_desc *descs)
                 PlanIt hit;
                 const int rc = lookup_plan(ctx, descs[i], false, hit);
                 if (rc != SB_OK) return rc;
-                if (group_plan_ok(ctx, hit->second)) cps[i] = &hit->second;
+                if (hit->second.plan.kind == PLAN_MAP) cps[i] = &hit->second; // (same cached plan <=> same shapes, strides, eltypes, program)
             }
         std::vector<char> taken((size_t)n, 0);
         for (int i = 0; i < n; ++i) {
@@ -939,7 +941,20 @@ extern "C" int sb_mapreduce_batch(sb_ctx *ctx, int n, const sb_desc *descs)
                         u.idx.push_back(j);
                         taken[j] = 1;
                     }
-                if (u.idx.size() >= 2) u.cp = cps[i];
+                if (u.idx.size() >= 2) { // the plan of a grouped launch is sized for many problems (DeviceInfo::grouped)
+                    PlanIt gh;
+                    const int rc = lookup_plan(ctx, descs[i], false, gh, true);
+                    if (rc != SB_OK) return rc;
+                    if (group_plan_ok(ctx, gh->second)) u.cp = &gh->second;
+                }
+            }
+            if (!u.cp && u.idx.size() >= 2) { // not groupable: independent single calls, one unit each (they overlap on the side streams)
+                for (int q : u.idx) {
+                    Unit one;
+                    one.idx.push_back(q);
+                    units.push_back(std::move(one));
+                }
+                continue;
             }
             units.push_back(std::move(u));
         }

@@ -13,7 +13,10 @@ namespace sb {
 // resident CTAs per SM the register allocator is asked to allow (value registers = NIN*EPT words of CT)
 template <class CT, int NIN, int EPT> struct MinBlocks {
     static constexpr int words = NIN * EPT * (int)(sizeof(CT) / 4);
-    static constexpr int value = words <= 32 ? 4 : (words <= 64 ? 2 : 1);
+    // (4-byte eltypes with <= 8 value words: the dense-copy kernels need 5 CTAs per SM -- 172 vs 189 us for a 2^27 Float32 copy
+    //  when the per-tile record registers pushed them to 52; the 8-byte EPT = 4 kernels are FASTER at 4 CTAs per SM: config 3
+    //  warm 3.21 vs 3.59 us)
+    static constexpr int value = (words <= 8 && sizeof(CT) == 4) ? 5 : (words <= 32 ? 4 : (words <= 64 ? 2 : 1));
 };
 
 template <class CT, int RC, int NIN, int EPT, bool UNIFORM, bool GROUP>

@@ -1482,7 +1482,7 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
     // 835 -> 697 us = 0.94 of peak).  The TMA ring keeps two-input maps (`(A .+ A') ./ 2`: 42.4 vs 46.3 us) and extents that
     // leave edge tiles, which the TMA unit clips for free (54^4: 31.9 vs 50.9 us; 3000^2: 24.7 vs 26.2 us).
     const bool lsu_pref_on = !std::getenv("SB_NO_PREFER_LSU") && !std::getenv("SB_NO_LSU_DESC") && nin == 1 && esz == 8;
-    const bool small_single = lsu_pref_on && elements * esz * 2 <= ((int64_t)32 << 20);
+    const bool small_single = lsu_pref_on && !dev.grouped && elements * esz * 2 <= ((int64_t)32 << 20);
     if (ept < 8 && !std::getenv("SB_FORCE_EPT") && !small_single && tma_candidate(c, P.prog.recipe, template_nin(P.prog.recipe, nin), uniform)) ept = 8;
     if (!std::getenv("SB_FORCE_EPT")) { // prefer the largest tile that can be filled without padding waste
         int best = ept, best_left = 1 << 30;

@@ -18,6 +18,7 @@ struct DeviceInfo {
     int sm_count = 148;        // B200
     int ctas_per_sm = 4;       // resident CTAs of THREADS threads assumed for grid sizing
     bool host_link = false;    // operands are pinned HOST memory accessed by the kernel (zero-copy): fuse aliased views from 2 views on
+    bool grouped = false;      // the plan serves a grouped launch (several problems of this shape in one grid): never "small"
 };
 
 struct KernelKey {
