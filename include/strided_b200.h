@@ -165,9 +165,10 @@ int sb_mapreduce(sb_ctx *ctx, const sb_desc *desc);
  * whatever the kernel does); the batch runs its INDEPENDENT map calls -- output byte range disjoint from every other
  * call's operands -- concurrently on side streams between a fork and a join on the ctx's stream, everything else
  * (reductions, chains such as B = f(A); C = g(B)) in order after the join.  Independent calls that share ONE plan (same
- * dims, strides, eltypes and program; only the base pointers differ) and take the TMA ring kernel are merged into a single
- * grouped launch of up to 16 problems (`sb_stats.grouped_calls`): a block of equal-shape `permutedims!` then streams at
- * HBM speed instead of paying one launch + one DRAM round trip per statement.  Results are the same as n sb_mapreduce calls
+ * dims, strides, eltypes and program; only the base pointers differ) are merged into a single grouped launch of up to 16
+ * problems (`sb_stats.grouped_calls`; TMA ring kernel, or the LSU kernel for copies / scalings / two-input sums): a block
+ * of equal-shape `permutedims!` then streams at HBM speed instead of paying one launch + one DRAM round trip per
+ * statement.  The group has its own cached plan, sized for all its problems.  Results are the same as n sb_mapreduce calls
  * in order.  Capturable in a CUDA graph (parallel branches) once a batch has run outside the capture.  The reference
  * issues one `_mapreduce_fuse!` per statement (src/mapreduce.jl:98); this is the entry a glue uses for a block of
  * independent `@strided` statements. */
