@@ -795,7 +795,14 @@ bool plan_tma(const Canon &c, const MapParams &P, const int *tdim, Plan &plan, c
             // a transposing operand with a single 128-byte row per box line (16 Float64 along its contiguous dim: what odd
             // extents such as 70^4 end up with) is faster through the LSU kernel: 105 vs 141 us on the 70^4 reversal
             // (profiles/r02_j_odd_extents_tma_vs_lsu_shift.txt); from 256-byte rows on the TMA ring wins (54^4: 33 vs 54 us)
-            if (b * esz < 256 && !std::getenv("SB_TMA_NARROW")) return false;
+            // -- for 8-byte elements.  4-byte elements are the other way round: their 2048-element tiles ([64, 32]) have
+            // 128-byte transposing rows by construction, and the ring beats the LSU kernel by 20-45 % once the problem
+            // is not launch-bound (Float32 `3 .* A'` 4096^2: 35.8 -> 24.5 us = 0.84, 8192^2 0.63 -> 0.90; `(A .+ A') ./ 2`
+            // 4000^2: 39.0 -> 29.1 us; 1000^2 loses: 3.42 -> 3.82 us; profiles/r02_y_f32_*).
+            int64_t total_elems = 1;
+            for (int d = 0; d < n; ++d) total_elems *= c.dims[d];
+            const bool narrow_ok = std::getenv("SB_TMA_NARROW") || (esz == 4 && !std::getenv("SB_NO_TMA_NARROW") && total_elems * esz * 2 >= ((int64_t)16 << 20));
+            if (b * esz < 256 && !narrow_ok) return false;
             o.swizzle = 1;
             o.nbox = b / ipb;
             o.inner_step = ipb;

@@ -181,3 +181,50 @@ def test_grouping_respects_dependencies_and_inplace():
     torch.cuda.synchronize()
     assert eng.stats()["grouped_calls"] == 0 and eng.stats()["launches"] == 2
     assert torch.equal(c, a)  # the reversal is an involution (benchmarks/benchtests.jl:40)
+
+
+@pytest.mark.parametrize("dtname", ["float64", "float32", "complex64"])
+def test_grouped_lsu_launch_odd_extents(dtname):
+    # odd extents cannot take the TMA ring: same-plan calls are merged into one launch of the LSU kernel (map_tile_group_kernel)
+    import torch
+    dt = getattr(torch, dtname)
+    dev = torch.device("cuda", 0)
+    eng = sb.get_engine(0)
+    m, nprob = 21, 5
+    sh = (m,) * 4
+    g = torch.Generator(device=dev)
+    g.manual_seed(31)
+    calls, checks = [], []
+    for _ in range(nprob):
+        a = torch.randn(m ** 4, dtype=dt, device=dev, generator=g) if not dt.is_complex else torch.view_as_complex(torch.randn(m ** 4, 2, dtype=torch.float32, device=dev, generator=g))
+        b = torch.zeros_like(a)
+        calls.append((P_COPY, 0, 0, 0.0, sh, [sb.StridedView(b, sh, _col(sh)), sb.StridedView(a, sh, _col(sh)).permutedims((3, 2, 1, 0))]))
+        checks.append((b, a.view(*sh).permute(3, 2, 1, 0).contiguous().view(-1)))
+    eng.reset_stats()
+    sb.run_batch(calls)
+    torch.cuda.synchronize()
+    st = eng.stats()
+    assert st["grouped_calls"] == nprob and st["launches"] == 1
+    for got, want in checks:
+        assert torch.equal(got, want)
+
+
+def test_grouped_lsu_two_input_sum():
+    # Z_i = X_i .+ Y_i' at 301^2 (odd: LSU kernel), six problems in one launch
+    import torch
+    dev = torch.device("cuda", 0)
+    eng = sb.get_engine(0)
+    n, nprob = 301, 6
+    g = torch.Generator(device=dev)
+    g.manual_seed(37)
+    Xs = [torch.randn(n * n, dtype=torch.float64, device=dev, generator=g) for _ in range(nprob)]
+    Ys = [torch.randn(n * n, dtype=torch.float64, device=dev, generator=g) for _ in range(nprob)]
+    Zs = [torch.zeros(n * n, dtype=torch.float64, device=dev) for _ in range(nprob)]
+    calls = [([A(0), A(1), F("add")], 0, 0, 0.0, (n, n), [sb.StridedView(z, (n, n), (1, n)), sb.StridedView(x, (n, n), (1, n)), sb.StridedView(y, (n, n), (1, n)).T])
+             for x, y, z in zip(Xs, Ys, Zs)]
+    eng.reset_stats()
+    sb.run_batch(calls)
+    torch.cuda.synchronize()
+    assert eng.stats()["grouped_calls"] == nprob and eng.stats()["launches"] == 1
+    for x, y, z in zip(Xs, Ys, Zs):
+        assert torch.equal(z, (x.view(n, n) + y.view(n, n).t()).contiguous().view(-1))
