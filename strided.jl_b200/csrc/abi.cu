@@ -69,6 +69,8 @@ void env_reload()
     c.jit_min_elements = e ? std::atoll(e) : (1ll << 18);
     c.jit_sync = std::getenv("SB_JIT_SYNC") != nullptr;
     c.no_group = std::getenv("SB_NO_GROUP") != nullptr;
+    const char *tm = std::getenv("SB_PLAN_TABLE_MB");
+    c.plan_table_mb = tm ? std::max(1ll, std::atoll(tm)) : 512;
 }
 cudaError_t ensure_dynamic_smem(const void *func, size_t smem)
 {
@@ -183,6 +185,8 @@ struct sb_ctx {
     // reduce partials
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
+    size_t table_bytes = 0; // device memory held by plan tables (tile orders, per-tile records, orbit items) of the cached plans
+    bool clear_pending = false;
     // occupancy cache: kernel function -> (smem -> blocks/SM)
     std::map<std::pair<const void *, size_t>, int> occ;
     // host staging pool (sb_mapreduce_host)
@@ -227,6 +231,14 @@ static void clear_plans(sb_ctx *ctx)
     for (auto &kv : ctx->plans)
         if (kv.second.dev_orbit) cudaFree(kv.second.dev_orbit);
     ctx->plans.clear();
+    ctx->table_bytes = 0;
+    ctx->clear_pending = false;
+}
+
+// plan tables over budget (lookup_plan): drop the cache at an API entry, where nobody holds plan pointers
+static void maybe_clear_plans(sb_ctx *ctx)
+{
+    if (ctx->clear_pending && !stream_is_capturing(ctx)) clear_plans(ctx);
 }
 
 static int set_err(sb_ctx *ctx, int code, const std::string &msg)
@@ -524,7 +536,7 @@ static int lookup_plan(sb_ctx *ctx, const sb_desc &desc, bool hostlink, PlanIt &
         rc = build_plan(desc, dinfo, fresh, err);
         if (rc != SB_OK) return set_err(ctx, rc, err);
         ctx->stats.plans_built++;
-        if (ctx->plans.size() > 4096 && !stream_is_capturing(ctx)) clear_plans(ctx);
+        if (ctx->plans.size() > 4096) ctx->clear_pending = true; // (dropped at the next API entry, see maybe_clear_plans)
         CachedPlan cp;
         cp.plan = std::move(fresh);
         const bool tables = !cp.plan.tile_order.empty() || !cp.plan.tile_desc.empty() || !cp.plan.orbit_items.empty() || !cp.plan.lsu_desc.empty();
@@ -535,6 +547,11 @@ static int lookup_plan(sb_ctx *ctx, const sb_desc &desc, bool hostlink, PlanIt &
             if (stream_is_capturing(ctx))
                 return set_err(ctx, SB_E_UNSUPPORTED, "first call of this plan inside a CUDA-graph capture: run the call once outside the capture (plan tables are uploaded on the first call)");
             // (a plain synchronous copy: nothing of this plan is in flight yet)
+            // (plan tables are a cache: beyond SB_PLAN_TABLE_MB = 512 MB per context everything is dropped and rebuilt on demand)
+            const size_t incoming = cp.plan.tile_order.size() * sizeof(int32_t) + cp.plan.tile_desc.size() * sizeof(TileDesc) +
+                                    cp.plan.orbit_items.size() * sizeof(OrbitItem) + cp.plan.lsu_desc.size() * sizeof(int64_t);
+            if (ctx->table_bytes + incoming > ((size_t)env_cache().plan_table_mb << 20)) ctx->clear_pending = true; // (dropped at the next API entry: callers may hold plan pointers)
+            ctx->table_bytes += incoming;
             auto upload = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
                 cudaError_t e = cudaMalloc(dst, bytes);
                 if (e == cudaSuccess) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
@@ -765,6 +782,7 @@ extern "C" int sb_mapreduce(sb_ctx *ctx, const sb_desc *desc)
     if (!ctx) return set_err(nullptr, SB_E_INVALID, "sb_mapreduce: null ctx");
     if (!desc) return set_err(ctx, SB_E_INVALID, "sb_mapreduce: null desc");
     std::lock_guard<std::mutex> lk(ctx->mu);
+    maybe_clear_plans(ctx);
     int rc = run_desc(ctx, *desc);
     if (rc != SB_OK) return rc;
     if (ctx->sync) {
@@ -873,6 +891,7 @@ extern "C" int sb_mapreduce_batch(sb_ctx *ctx, int n, const sb_desc *descs)
     if (!ctx) return set_err(nullptr, SB_E_INVALID, "sb_mapreduce_batch: null ctx");
     if (n < 0 || (n > 0 && !descs)) return set_err(ctx, SB_E_INVALID, "sb_mapreduce_batch: bad arguments");
     std::lock_guard<std::mutex> lk(ctx->mu);
+    maybe_clear_plans(ctx);
     cudaSetDevice(ctx->device);
     std::vector<char> parallel((size_t)n, 0);
     {

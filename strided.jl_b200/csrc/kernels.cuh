@@ -16,6 +16,7 @@ struct EnvCache {
     long long jit_min_elements = 1 << 18;  // SB_JIT_MIN_ELEMENTS
     bool jit_sync = false;                 // SB_JIT_SYNC: block on the NVRTC compile instead of compiling in the background
     bool no_group = false;                 // SB_NO_GROUP: sb_mapreduce_batch never merges same-plan calls into one launch
+    long long plan_table_mb = 512;         // SB_PLAN_TABLE_MB: device memory the plan tables of one context may hold before the cache is dropped
 };
 EnvCache &env_cache();  // abi.cu
 void env_reload();      // abi.cu

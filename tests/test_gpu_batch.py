@@ -228,3 +228,27 @@ def test_grouped_lsu_two_input_sum():
     assert eng.stats()["grouped_calls"] == nprob and eng.stats()["launches"] == 1
     for x, y, z in zip(Xs, Ys, Zs):
         assert torch.equal(z, (x.view(n, n) + y.view(n, n).t()).contiguous().view(-1))
+
+
+def test_plan_table_budget_drops_the_cache(monkeypatch):
+    # plan tables (tile orders, per-tile records) are a cache with a device-memory budget: over budget the whole plan cache is
+    # dropped at the next API entry and rebuilt on demand -- results stay right, plans are simply built again
+    import torch
+    dev = torch.device("cuda", 0)
+    eng = sb.get_engine(0)
+    monkeypatch.setenv("SB_PLAN_TABLE_MB", "1")
+    eng.reload_env()
+    try:
+        eng.reset_stats()
+        for rep in range(2):
+            for m in (64, 72, 80, 88):  # four shapes with 0.2 ... 0.7 MB of per-tile records and tile orders each: 1.7 MB together
+                sh = (m,) * 4
+                a = torch.randn(m ** 4, dtype=torch.float64, device=dev)
+                b = torch.zeros_like(a)
+                sb.copy_(sb.StridedView(b, sh, _col(sh)), sb.StridedView(a, sh, _col(sh)).permutedims((3, 2, 1, 0)))
+                torch.cuda.synchronize()
+                assert torch.equal(b, a.view(*sh).permute(3, 2, 1, 0).contiguous().view(-1))
+        assert eng.stats()["plans_built"] > 4  # the second round had to plan again at least once
+    finally:
+        monkeypatch.delenv("SB_PLAN_TABLE_MB")
+        eng.reload_env()
