@@ -550,9 +550,20 @@ bool build_hot_order(const MapParams &P, const bool *hot, std::vector<int32_t> &
 {
     const int n = P.ndim;
     if (P.ntiles > (1 << 22) || P.ntiles < 2) return false;
+    // hot dims with the SHORTEST tile run first: neighbouring tiles then complete the short runs into long ones within a wave
+    // (rotation `permutedims!(B, A, (2,3,4,1))` of 70^4: tile [128, 16], the input's 128-byte runs are completed to 560-byte
+    // rows by the 5 tiles along dim 1, which ran 2680 tiles apart in the natural order); ties keep the output's dim first
     int perm[MAXD], np = 0;
     for (int d = 0; d < n; ++d)
         if (hot[d]) perm[np++] = d;
+    std::stable_sort(perm, perm + np, [&](int a, int b) { return P.tile_b[a] < P.tile_b[b]; });
+    // ... as long as few tiles cover that dim (the rows are then completed within one wave: 70^4 rotation 95.4 -> 65.9 us,
+    // 100^4 418 -> 269 us = 0.91); a long dim counted first loses (5001^2 transpose 69.1 -> 71.9 us): output's dim first then
+    if (np > 0 && P.ntile[perm[0]] > 32) {
+        np = 0;
+        for (int d = 0; d < n; ++d)
+            if (hot[d]) perm[np++] = d;
+    }
     for (int d = 0; d < n; ++d)
         if (!hot[d]) perm[np++] = d;
     // identical to the natural order unless a multi-tile dim is overtaken by a later multi-tile dim
