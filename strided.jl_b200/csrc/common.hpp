@@ -189,7 +189,7 @@ struct MapParams {
     int64_t ntiles;
     const int32_t *tile_order; // optional device table: launch position -> tile id (alias-aware order)
     const TileDesc *tile_desc; // optional device table (TMA path): launch position -> precomputed tile record
-    // optional device table (LSU kernel): launch position -> {tile id | full << 31, byte offset of the tile origin in operand
+    // optional device table (LSU kernel): launch position -> {tile id | full << 31 | packed edge mask << 32, byte offset of the tile origin in operand
     // 0, 1, ..., nops-1} as nops + 1 int64 words.  ncu on the 91^4 reversal showed ~400 instructions per thread and tile,
     // most of them the per-tile decode (4 magic divisions, 64-bit multiply-adds per operand and dim, shifted-tile
     // corrections) that every thread repeats: with the record it is one uniform load and one add per operand.

@@ -69,7 +69,7 @@ template <int NOPS> SB_HD void map_tile_record(const MapParams &P, uint32_t pos,
 template <int NOPS> SB_HD void map_tile_from_record(const MapParams &P, const MapThread<NOPS> &th, const int64_t (&r)[NOPS + 1], MapTile<NOPS> &tl)
 {
     const uint32_t w = (uint32_t)r[0];
-    tl.id = w & 0x7fffffffu;
+    tl.id = (uint32_t)((uint64_t)r[0] >> 32); // with a record, `id` carries the tile's packed edge mask (map_tile_rem, precomputed)
     tl.full = (w >> 31) != 0;
 #pragma unroll
     for (int k = 0; k < NOPS; ++k) tl.ptr[k] = P.base[k < P.nops ? k : 0] + (th.g_toff[k] + (k < P.nops ? r[1 + k] : 0));
@@ -182,7 +182,7 @@ SB_HD void map_phase1(const MapParams &P, const MapThread<NIN + 1> &th, const Ma
     } else {
         // masked tile: an edge tile (mask from the tile's remaining extents) or a balanced tile (plan-constant mask; whole
         // 16-byte groups are valid or not, the planner keeps the balanced extents multiples of V)
-        const uint32_t rg = tl.full ? P.urg : map_tile_rem(P, tl.id);
+        const uint32_t rg = tl.full ? P.urg : (P.lsu_desc ? tl.id : map_tile_rem(P, tl.id));
 #pragma unroll
         for (int k = 1; k <= NIN; ++k) {
             if (VEC && tl.full && k < P.nops && P.gvec[k]) {
@@ -265,7 +265,7 @@ SB_HD void map_phase2(const MapParams &P, const MapThread<NIN + 1> &th, const Ma
             store_elem<CT, UNIFORM>(ob + P.g_joff[0][j], P.dtype[0], P.conj[0], fn.template eval<NIN>(P.prog, a));
         }
     } else {
-        const uint32_t rg = tl.full ? P.urg : map_tile_rem(P, tl.id);
+        const uint32_t rg = tl.full ? P.urg : (P.lsu_desc ? tl.id : map_tile_rem(P, tl.id));
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
             CT a[NIN];

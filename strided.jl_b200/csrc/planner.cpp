@@ -1448,7 +1448,7 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
         return (double)(((c.dims[i] + t - 1) / t) * t) / (double)c.dims[i];
     };
     int lim[MAXD];
-    double max_waste = balanced ? 1.45 : 1.2;
+    double max_waste = 1.2; // (balanced mode: idle-lane factor of a box; larger boxes with more idle lanes measured slower)
     if (const char *e = std::getenv(balanced ? "SB_BAL_WASTE" : "SB_WASTE")) max_waste = std::max(1.0, std::atof(e)); // tuning knob
     for (int i = 0; i < n; ++i) {
         const int lo = hot[i] ? std::min(cap[i], minrun_bits) : 0;
@@ -1771,7 +1771,10 @@ int plan_map(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &err
                     r[1 + k] += (int64_t)cd * P.tstep[k][d] - (shifted ? (int64_t)P.excess[d] * P.strides[k][d] * dtype_size(P.dtype[k]) : 0);
             }
             if (full) w |= 0x80000000u;
-            r[0] = (int64_t)w;
+            // edge tiles carry their packed mask: no per-tile decode in the kernel at all (a dim shorter than its box -- 54 in a
+            // 64-wide tile -- makes EVERY tile an edge tile: Float32 54^4 reversal 49.1 -> 17 us)
+            const uint32_t rg = full ? 0u : map_tile_rem(P, w & 0x7fffffffu);
+            r[0] = (int64_t)(((uint64_t)rg << 32) | (uint64_t)w);
         }
     }
     plan.elements = 1;
@@ -2112,13 +2115,20 @@ int build_plan(const sb_desc &d, const DeviceInfo &dev, Plan &plan, std::string 
     // dim.  Balanced tiles (MapParams::umask) remove the recomputation -- and measure the SAME or slower (reversal permute of
     // 70^4: 105.9 us with 14-of-16 balanced tiles vs 105.6 us shifted; 130.5 us with 24-of-32 tiles;
     // profiles/r02_q_odd_extents_balanced.txt): the kernel is bound by per-tile instruction issue and the latency of short
-    // unaligned runs, not by L2<->SM bytes.  Kept as an opt-in tuning knob (SB_BALANCED=1), off by default.
-    if (rc == SB_OK && plan.kind == PLAN_MAP && !plan.tma_ok && !plan.orbit_ok && std::getenv("SB_BALANCED")) {
+    // unaligned runs, not by L2<->SM bytes.  Default only where a dim is shorter than its box; SB_BALANCED=1 forces it.
+    if (rc == SB_OK && plan.kind == PLAN_MAP && !plan.tma_ok && !plan.orbit_ok && !std::getenv("SB_NO_BALANCED")) {
         const MapParams &P = plan.map;
         double w_pow2 = 1.0; // work of the power-of-two tiling relative to the array (recomputed or masked coordinates)
+        bool short_dim = false; // a dim shorter than its box: EVERY tile is an edge tile of the power-of-two tiling
         for (int i = 0; i < P.ndim; ++i)
-            if (P.tile_b[i] > 1) w_pow2 *= (double)((int64_t)P.ntile[i] * P.tile_b[i]) / (double)c.dims[i];
-        if (w_pow2 > 1.10) {
+            if (P.tile_b[i] > 1) {
+                w_pow2 *= (double)((int64_t)P.ntile[i] * P.tile_b[i]) / (double)c.dims[i];
+                short_dim = short_dim || c.dims[i] < P.tile_b[i];
+            }
+        // measured with per-tile records (profiles/r02_z_f32_odd_balanced_*.txt, r02_z_mask_records.txt): with a short dim the
+        // balanced plan wins clearly (Float32 54^4 reversal 31.5 -> 17.7 us: the plan-constant mask replaces the edge path of
+        // every tile); without one it is within +-7 % of the shifted tiling (41^4 +7 %, 70^4 -1 %) and stays opt-in
+        if ((short_dim && w_pow2 > 1.02) || (std::getenv("SB_BALANCED") && w_pow2 > 1.10)) {
             Plan alt;
             std::string err2;
             if (plan_map(c, dev, alt, err2, true) == SB_OK && alt.map.umask) plan = std::move(alt);
