@@ -1895,13 +1895,35 @@ int plan_reduce(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &
     });
     int tb[MAXD] = {0};
     int used = 0, ntdims = 0;
+    // A KEPT dim takes at most a 2 KB run of the tile and at most 1/8 of all outputs: `sum(A; dims=2)` of a column-major
+    // 4096^2 matrix used to give all 2048 tile elements to the contiguous kept dim -- 2 output tiles, so 293 splits of the
+    // reduced dim to fill the GPU, and ONE last-arriving CTA per output tile folding 293 x 2048 partials with one dependent L2
+    // round trip per eight outputs: 1011 us = 0.02 of peak.  With 256 outputs x 8 reduced rows per tile (16 output tiles, 37
+    // splits) and a thread-per-output fold: 29 us = 0.70; 8192^2 771 -> 124 us; 256^3 dims=2 105 -> 35 us; 128 x 512 x 512
+    // dims=(2,3) 136 -> 53 us; Float32 8192^2 571 -> 74 us (profiles/r02_z_reduce_dims_*.txt: no single cap wins everywhere,
+    // the cost follows the number of splits).
+    int kcap_bytes = 2048;
+    if (const char *e = std::getenv("SB_KEPT_CAP_BYTES")) kcap_bytes = std::max(64, std::atoi(e)); // tuning knob
+    int64_t total_kept = 1;
+    for (int i = 0; i < c.nkept; ++i) total_kept *= c.dims[i];
+    const int kcap = std::max(3, std::min(ilog2_ceil(kcap_bytes / esz), ilog2_ceil(total_kept) - 3));
     for (int q = 0; q < n && used < ebits && ntdims < MAXTD; ++q) {
         const int i = ord[q];
-        const int b = std::min(ilog2_ceil(c.dims[i]), ebits - used);
+        int b = std::min(ilog2_ceil(c.dims[i]), ebits - used);
+        if (i < c.nkept && !std::getenv("SB_NO_KEPT_CAP")) b = std::min(b, kcap);
         if (b == 0) continue;
         tb[i] = b;
         used += b;
         ntdims++;
+    }
+    for (int q = 0; q < n && used < ebits; ++q) { // bits nobody else wanted go back to the capped kept dims
+        const int i = ord[q];
+        if (tb[i] == 0) continue;
+        const int more = std::min(ilog2_ceil(c.dims[i]) - tb[i], ebits - used);
+        if (more > 0) {
+            tb[i] += more;
+            used += more;
+        }
     }
     if (used < ebits) { // pad along the fastest dim (masked)
         if (ntdims == 0) ntdims = 1;

@@ -314,6 +314,29 @@ def odd_extent_cases():
     return out
 
 
+# Partial reductions with MANY outputs along the contiguous dim (`sum(A; dims=2)` of a column-major matrix, Base.mapreducedim!
+# through src/mapreduce.jl:74-96): tiles with many outputs, split reduced dim, thread-per-output fold of the partials.
+def many_output_reduction_cases(n=768):
+    out = []
+    for dt in (np.float64, np.float32, np.complex64):
+        rng = _rng("manyout", np.dtype(dt).name)
+        nm = np.dtype(dt).name
+        tol = 2e-4 if dt in (np.float32, np.complex64) else 1e-11
+        a = (rand(rng, n * n, dt) - 0.5).astype(dt)
+        M = ViewSpec.dense(1, (n, n))
+        out.append(Case(f"rowsum_{n}_{nm}", [np.full(n, 2, dt), a], [ViewSpec(0, 0, (n, n), (1, 0)), M], P_COPY, op=1, rtol=tol))
+        out.append(Case(f"rowsum_init0_abs2_{n}_{nm}", [np.full(n, 2, dt), a], [ViewSpec(0, 0, (n, n), (1, 0)), M], [A(0), F("abs2")], op=1, initop=1, rtol=tol))
+        out.append(Case(f"colsum_{n}_{nm}", [np.zeros(n, dt), a], [ViewSpec(0, 0, (n, n), (0, 1)), M], P_COPY, op=1, rtol=tol))
+        m = max(n // 8, 8)
+        a3 = (rand(rng, m * m * m, dt) - 0.5).astype(dt)
+        T = ViewSpec.dense(1, (m, m, m))
+        out.append(Case(f"sum_dim2_{m}^3_{nm}", [np.zeros(m * m, dt), a3], [ViewSpec(0, 0, (m, m, m), (1, 0, m)), T], P_COPY, op=1, rtol=tol))
+        out.append(Case(f"sum_dims23_{m}^3_{nm}", [np.zeros(m, dt), a3], [ViewSpec(0, 0, (m, m, m), (1, 0, 0)), T], P_COPY, op=1, rtol=tol))
+        if np.dtype(dt).kind == "f":
+            out.append(Case(f"rowmax_{n}_{nm}", [np.full(n, -9, dt), a], [ViewSpec(0, 0, (n, n), (1, 0)), M], [A(0), F("abs")], op=4))
+    return out
+
+
 # README.md:85-89 / :133-137: the compute-bound benchmark expression  B .= A .* exp.(-2 .* A) .+ sin.(A .* A)
 # (the same parent captured four times: four identical views, nothing to fuse, one pass over A)
 def readme_compute_bound_cases(n=1000):
@@ -342,5 +365,6 @@ def all_cases(scale=1.0):
     cases += reduction_shape_cases(4 if s >= 1 else 1)
     cases += edge_cases()
     cases += odd_extent_cases()
+    cases += many_output_reduction_cases(768 if s >= 1 else 160)
     cases += readme_compute_bound_cases(max(int(1000 * s), 64))
     return cases
