@@ -1907,10 +1907,17 @@ int plan_reduce(const Canon &c, const DeviceInfo &dev, Plan &plan, std::string &
     int64_t total_kept = 1;
     for (int i = 0; i < c.nkept; ++i) total_kept *= c.dims[i];
     const int kcap = std::max(3, std::min(ilog2_ceil(kcap_bytes / esz), ilog2_ceil(total_kept) - 3));
+    // The mirror case: the contiguous dim is REDUCED and there are many outputs (`sum(A; dims=1)`, column sums): giving it all
+    // 2048 tile elements makes one CTA per output (4096 tiny CTAs for 4096^2).  A 2 KB run leaves bits for the kept dims.
+    // Column sums: 4096^2 38.4 -> 31.8 us, 8192^2 112 -> 100 us (0.82), Float32 8192^2 84.8 -> 61.7 us
+    // (profiles/r02_z_reduce_dims_rcap.txt).  SB_RED_CAP_BYTES=0 switches it off.
+    int rcap = ilog2_ceil(2048 / esz);
+    if (const char *e = std::getenv("SB_RED_CAP_BYTES")) rcap = std::atoi(e) > 0 ? ilog2_ceil(std::max(64, std::atoi(e)) / esz) : 0;
     for (int q = 0; q < n && used < ebits && ntdims < MAXTD; ++q) {
         const int i = ord[q];
         int b = std::min(ilog2_ceil(c.dims[i]), ebits - used);
         if (i < c.nkept && !std::getenv("SB_NO_KEPT_CAP")) b = std::min(b, kcap);
+        if (i >= c.nkept && q == 0 && rcap > 0 && c.nkept > 0) b = std::min(b, rcap); // (see rcap above)
         if (b == 0) continue;
         tb[i] = b;
         used += b;

@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-SB_JIT_SYNC=1 timeout 900 python tools/exp_probe.py 2>&1 | grep "v'\|README\|axpy" > gpurun_out/r2z_probe_jit_sync.txt; cat gpurun_out/r2z_probe_jit_sync.txt
+timeout 600 python tools/exp_reduce_dims.py > gpurun_out/r2z_reduce_dims_final.txt 2>&1; cat gpurun_out/r2z_reduce_dims_final.txt
