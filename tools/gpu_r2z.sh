@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/last_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/last_pytest_gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/last_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/last_smoke.log
-timeout 600 python bench.py --steps 50 --warmup 5 --no-configs --no-sharded 2>/dev/null | tail -1 | cut -c1-260
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -x -q -k "rowsum or colsum or sum_dim or rowmax or sum_135 or initop" > gpurun_out/r02_san_memcheck_reductions.log 2>&1; echo "memcheck rc=$?"; tail -3 gpurun_out/r02_san_memcheck_reductions.log
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -x -q -k "rowsum_768_float64 or colsum_768_float64 or sum_dim2" > gpurun_out/r02_san_racecheck_reductions.log 2>&1; echo "racecheck rc=$?"; tail -3 gpurun_out/r02_san_racecheck_reductions.log
