@@ -623,7 +623,9 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc, const PeerLink *peer = nul
     const JitKernel *jk = nullptr;
     // (plans with an alias-fused orbit variant keep the in-kernel interpreter: the orbit kernel is bound by its memory
     //  request rate, not by instruction issue, and beats the generic kernel + JIT by 2-3x on aliased views)
-    if (plan.key.recipe == RC_INTERP && jit_enabled() && !(plan.kind == PLAN_MAP && plan.orbit_ok)) {
+    // (... and reductions for which the streamed kernel has its own functor: faster than the NVRTC-specialised tile kernel)
+    if (plan.key.recipe == RC_INTERP && jit_enabled() && !(plan.kind == PLAN_MAP && plan.orbit_ok) &&
+        !(plan.kind == PLAN_REDUCE && plan.stream_ok && plan.stream_recipe != RC_INTERP)) {
         const int64_t thr = (int64_t)env_cache().jit_min_elements;
         if (plan.elements >= thr)
             jk = jit_get(plan.kind == PLAN_MAP ? JIT_MAP : JIT_REDUCE, plan.key, plan.kind == PLAN_MAP ? plan.map.prog : plan.red.prog,
@@ -739,7 +741,12 @@ static int run_desc(sb_ctx *ctx, const sb_desc &desc, const PeerLink *peer = nul
         if (!jk && plan.stream_ok) { // streamed complete reduction: dense inputs, 16-byte aligned at bind time
             bool aligned = true;
             for (int q = 1; q <= plan.stream.nin; ++q) aligned = aligned && (((uintptr_t)plan.red.base[q] & 15u) == 0);
-            const StreamEntry *sk = aligned ? find_stream_kernel(plan.key) : nullptr;
+            KernelKey skey = plan.key;
+            if (plan.stream_recipe != RC_INTERP) { // a functor only the streamed kernel has (common.hpp RC_S_*)
+                skey.recipe = plan.stream_recipe;
+                skey.nin = plan.stream.nin;
+            }
+            const StreamEntry *sk = aligned ? find_stream_kernel(skey) : nullptr;
             if (sk) {
                 StreamArgs sa;
                 std::memset(&sa, 0, sizeof sa);

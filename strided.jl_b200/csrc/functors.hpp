@@ -49,6 +49,13 @@ template <class CT> struct ElemFn<CT, RC_ABS2> {
     template <int NIN> SB_HD CT eval(const Program &, const CT *a) const { return call1(FN_ABS2, a[0]); }
 };
 
+template <class CT> struct ElemFn<CT, RC_S_ABS> {
+    template <int NIN> SB_HD CT eval(const Program &, const CT *a) const { return call1(FN_ABS, a[0]); }
+};
+template <class CT> struct ElemFn<CT, RC_S_MUL2> {
+    template <int NIN> SB_HD CT eval(const Program &, const CT *a) const { return call2(FN_MUL, a[0], a[NIN > 1 ? 1 : 0]); }
+};
+
 // Generic interpreter.  The value stack lives in registers: depth is bounded by 4 (the planner rejects
 // deeper programs with SB_E_UNSUPPORTED) and pushes/pops shift a fixed window, so no local memory is used.
 template <class CT> struct ElemFn<CT, RC_INTERP> {

@@ -8,6 +8,8 @@ const StreamEntry *stream_table(int *n)
         SB_STREAM_ENTRY(double, F64, RC_COPY, 1),      SB_STREAM_ENTRY(double, F64, RC_ABS2, 1),
         SB_STREAM_ENTRY(double, F64, RC_INTERP, 1),    SB_STREAM_ENTRY(double, F64, RC_INTERP, 2),
         SB_STREAM_ENTRY(double, F64, RC_INTERP, 3),
+        SB_STREAM_ENTRY(double, F64, RC_S_ABS, 1),     SB_STREAM_ENTRY(double, F64, RC_S_MUL2, 2),
+        SB_STREAM_ENTRY(float, F32, RC_S_ABS, 1),      SB_STREAM_ENTRY(float, F32, RC_S_MUL2, 2),
         SB_STREAM_ENTRY(float, F32, RC_COPY, 1),       SB_STREAM_ENTRY(float, F32, RC_ABS2, 1),
         SB_STREAM_ENTRY(float, F32, RC_INTERP, 1),     SB_STREAM_ENTRY(float, F32, RC_INTERP, 2),
         SB_STREAM_ENTRY(float, F32, RC_INTERP, 3),

@@ -1789,7 +1789,8 @@ bool stream_instantiated(int ct, int recipe, int nin_t)
 {
     if (recipe == RC_INTERP) return nin_t >= 1 && nin_t <= 3;
     if (recipe == RC_COPY) return nin_t == 1;
-    if (recipe == RC_ABS2) return nin_t == 1 && (ct == F32 || ct == F64);
+    if (recipe == RC_ABS2 || recipe == RC_S_ABS) return nin_t == 1 && (ct == F32 || ct == F64);
+    if (recipe == RC_S_MUL2) return nin_t == 2 && (ct == F32 || ct == F64);
     return false;
 }
 
@@ -1802,7 +1803,13 @@ void plan_stream(const Canon &c, const DeviceInfo &dev, bool uniform, Plan &plan
     const int nin = c.nops - 1, esz = dtype_size(c.ct);
     if (c.ndim != c.nkept + 1 || c.nkept > STREAM_MAXKD || !uniform || nin < 1 || nin > 3) return;
     const int r = c.nkept; // the (fused) reduced dim
-    if (!stream_instantiated(plan.key.ct, plan.key.recipe, plan.key.nin)) return;
+    plan.stream_recipe = RC_INTERP;
+    if (plan.key.recipe == RC_INTERP && !std::getenv("SB_NO_STREAM_FUNCTORS")) { // functors of the streamed kernel only (common.hpp RC_S_*)
+        const Tok *t = c.tok;
+        if (nin == 1 && c.ntok == 2 && tok_arg(t[0], 0) && tok_call(t[1], FN_ABS) && stream_instantiated(plan.key.ct, RC_S_ABS, 1)) plan.stream_recipe = RC_S_ABS;
+        if (nin == 2 && c.ntok == 3 && tok_arg(t[0], 0) && tok_arg(t[1], 1) && tok_call(t[2], FN_MUL) && stream_instantiated(plan.key.ct, RC_S_MUL2, 2)) plan.stream_recipe = RC_S_MUL2;
+    }
+    if (plan.stream_recipe == RC_INTERP && !stream_instantiated(plan.key.ct, plan.key.recipe, plan.key.nin)) return;
     StreamParams &S = plan.stream;
     std::memset(&S, 0, sizeof S);
     // interleaved mode: ONE kept dim that is the innermost, contiguous dim of every input, the reduced dim dense on top of
@@ -2230,7 +2237,7 @@ std::string describe_plan(const Plan &p)
            << ",\"nout_tile\":" << P.nout_tile << ",\"nred_tile\":" << P.nred_tile
            << ",\"warp_per_output\":" << P.warp_per_output << ",\"scratch_bytes\":" << p.scratch_bytes;
         if (p.stream_ok)
-            os << ",\"stream\":{\"grid\":" << p.stream_grid << ",\"nout\":" << p.stream.nout << ",\"interleaved\":" << p.stream.inter_g << ",\"chunk_bytes\":" << p.stream.chunk_bytes << ",\"nstage\":" << p.stream.nstage
+            os << ",\"stream\":{\"functor\":" << p.stream_recipe << ",\"grid\":" << p.stream_grid << ",\"nout\":" << p.stream.nout << ",\"interleaved\":" << p.stream.inter_g << ",\"chunk_bytes\":" << p.stream.chunk_bytes << ",\"nstage\":" << p.stream.nstage
                << ",\"nchunks\":" << p.stream.nchunks << ",\"smem_bytes\":" << p.stream_smem_bytes << "}";
     }
     os << "}";

@@ -54,6 +54,7 @@ struct Plan {
     } tma_global[TMA_MAXIN];
     int64_t tma_smem_bytes = 0;
     std::vector<TileDesc> tile_desc; // per-tile records in launch order (uploaded with the plan)
+    int stream_recipe = 0;           // RC_INTERP, or a functor only the streamed reduction has (RC_S_ABS, RC_S_MUL2)
     std::vector<int64_t> lsu_desc;   // per-tile records of the LSU map kernel (MapParams::lsu_desc), launch order
     // alias-fused ("orbit") variant: all inputs are permuted views of one parent (see common.hpp).  Preferred over the
     // TMA ring when available; needs 16-byte aligned bases and an output that does not overlap the parent (bind time).
